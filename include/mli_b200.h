@@ -1,0 +1,207 @@
+/*
+ * mli_b200.h -- C ABI of the B200-native (sm_100a) paged-attention decode path that drops in for
+ * xyg-coder/min_llm_inference.  Plain pointers and sizes only; every pointer named *_dev / every
+ * tensor argument is a DEVICE pointer unless the comment says HOST.  All functions return 0 on
+ * success and a negative mli_status on failure; mli_last_error() gives the text.  Nothing here
+ * falls back to the CPU: without a CUDA device every compute entry point fails with MLI_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces (file:line under /root/reference).
+ * The C++ mirror of the reference's classes (Tensor, *Layer, *InferenceModel, start_*_engine ...)
+ * lives in min_llm_inference_b200/host/ and is implemented on top of exactly these calls.
+ *
+ * Data contracts (reference include/utils.h:32-76, include/constants.h:3-18):
+ *   page        float[16][3][d]   sub-row 0 = input embedding, 1 = K, 2 = V
+ *   page_table  float*[B][S/16]   raw device pointers; entries past a row's allocation are never read
+ *   lengths     int[B]            0 = empty row; mutated by the decoder stage
+ *   weights     float[d][d]       row-major [in, out] (y = x . W)
+ *   emb_table   float[V][d], pos_table float[S][d]
+ *   tokens      EOF = 1023, empty-row marker = -1
+ *   d % 4 == 0, S % 16 == 0, 1 <= n_forward_rounds <= 16
+ */
+#ifndef MLI_B200_H
+#define MLI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLI_PAGE_BLOCK_SIZE 16
+#define MLI_EOF_TOKEN_ID 1023
+#define MLI_EMPTY_ROW_TOKEN_ID (-1)
+#define MLI_DEFAULT_INIT_NUM_BLOCKS 4
+
+typedef enum {
+    MLI_OK = 0,
+    MLI_ERR_CUDA = -1,      /* CUDA runtime/driver failure ("Cuda Failure" in the reference, src/utils.cpp:5-11) */
+    MLI_ERR_ARG = -2,       /* contract violation (the reference asserts) */
+    MLI_ERR_NO_BLOCKS = -3, /* "No enough block memories to return" (src/paged_item_storage.cpp:145-147) */
+    MLI_ERR_UNSUPPORTED = -4,
+    MLI_ERR_STATE = -5
+} mli_status;
+
+typedef struct mli_ctx mli_ctx; /* opaque: stream, SM count, workspaces, cached TMA descriptors */
+
+typedef enum {
+    /* how the dense contractions (latest-token QKV, prefill, logits) are computed */
+    MLI_OPT_GEMM_MODE = 1,        /* 0 = tcgen05 3xTF32 (tensor cores, TMEM accumulators; default when
+                                         available), 1 = SIMT fp32 with the reference's k-ascending
+                                         FMA order (bit-exact with the reference's naive kernels) */
+    MLI_OPT_ATTN_CHUNK_PAGES = 2, /* KV pages per split of the fused decode attention; 0 = auto */
+    MLI_OPT_ATTN_CTAS_PER_SM = 3  /* persistent CTAs per SM for the fused decode attention; 0 = auto */
+} mli_option;
+
+/* ---- context --------------------------------------------------------------------------- */
+int mli_ctx_create(mli_ctx** out, int device, void* cuda_stream /* cudaStream_t, NULL = default */);
+int mli_ctx_destroy(mli_ctx* ctx);
+int mli_ctx_set_stream(mli_ctx* ctx, void* cuda_stream);
+int mli_ctx_set_option(mli_ctx* ctx, int option, int value);
+int mli_ctx_get_option(mli_ctx* ctx, int option, int* value);
+int mli_ctx_synchronize(mli_ctx* ctx);
+const char* mli_last_error(void);
+const char* mli_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it) */
+long long mli_kernel_launch_count(void);
+
+/* ---- paged stages ------------------------------------------------------------------------ */
+/* replaces launch_paged_attention_encoder_kernel (include/kernels/encoder.h:21-25,
+ * src/kernels/encoder.cu:102-147): new rows, j < L: page[j].inp = E[tok_j] + P[j] */
+int mli_paged_encoder(mli_ctx* ctx, const float* emb_table, const float* pos_table, const int* inp,
+                      float** page_table, const int* lengths, const int* new_item_indices,
+                      int n_batch, int n_sequence, int emb_dim, int n_new_items);
+
+/* replaces launch_fill_new_k_v_cache_paged_attention{,_warp_tiling}
+ * (include/kernels/paged_attention.h:28-30, :65-67; src/kernels/paged_attention.cu:20-115,
+ * src/kernels/paged_attention_cublas.cu:112-246): prefill K,V of new rows into their pages */
+int mli_prefill_kv_paged(mli_ctx* ctx, float** page_table, const int* new_batch_idx,
+                         const int* lengths, const float* wk, const float* wv, int n_new_items,
+                         int n_batch, int n_sequence, int emb_dim);
+
+/* replaces launch_get_latest_k_q_v_paged_attention{,_cublas} (paged_attention.h:32-35, :57-63;
+ * paged_attention.cu:126-199, paged_attention_cublas.cu:16-99): x = page[L-1].inp;
+ * k,v -> same page, q -> q_output[B,d]; rows with L == 0 untouched */
+int mli_qkv_latest_paged(mli_ctx* ctx, float** page_table, const int* lengths, const float* wk,
+                         const float* wq, const float* wv, float* q_output, int n_batch,
+                         int n_sequence, int emb_dim);
+
+/* replaces launch_qkt_paged_attention + launch_softmax_in_place_with_lengths +
+ * launch_softmax_v_paged_attention (paged_attention.h:37-43; paged_attention.cu:208-345;
+ * self_attention_inference_optimized.cu:191-242) with ONE fused, length-aware, split-KV kernel.
+ * attention_result[B,d]; rows with L == 0 get zeros.  softmax_out may be NULL; when given it
+ * receives the [B,S] probabilities the reference leaves in qkt_output (zeros past L). */
+int mli_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_table,
+                               const int* lengths, float* attention_result, float* softmax_out,
+                               int n_batch, int n_sequence, int emb_dim);
+
+/* replaces paged_attention / paged_attention_with_cublas (paged_attention.h:17-26, :46-55;
+ * paged_attention.cu:358-377): prefill(new rows) -> latest QKV -> fused decode attention.
+ * qkt_output may be NULL (the fused kernel needs no [B,S] scratch). */
+int mli_paged_attention(mli_ctx* ctx, float** page_table, const int* lengths, const float* wk,
+                        const float* wq, const float* wv, const int* new_batch_idx, float* q_output,
+                        float* qkt_output, float* attention_result, int n_new_items, int n_batch,
+                        int n_sequence, int emb_dim);
+
+/* replaces launch_paged_attention_decoder_multi_rounds / ..._cublas_... (include/kernels/decoder.h:27-37;
+ * src/kernels/decoder.cu:128-255): logits = attn . E^T, device-rule argmax, token ->
+ * decoder_result[r*n_decoder_results + i_decoder], lengths update, next embedding into page[L].
+ * emb_score[B,V] may be NULL (logits then stay in an internal workspace). */
+int mli_paged_decoder(mli_ctx* ctx, const float* batch_result, const float* emb_table,
+                      float* emb_score, const float* pos_table, float** page_table, int* lengths,
+                      int* decoder_result, int n_batch, int n_vocab, int n_sequence, int emb_dim,
+                      int n_decoder_results, int i_decoder);
+
+/* replaces PagedAttentionInferenceModel::forward / PagedAttentionCublasInferenceModel::forward
+ * (include/inference_model.h:34-74, src/inference_model.cpp:52-124): n_forward_rounds x
+ * (encoder -> attention -> decoder); new rows only in round 0.  attention_result[B,d] and
+ * q_output[B,d] are caller scratch (the reference's layer-owned tensors); may be NULL. */
+int mli_paged_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new_item_indices,
+                      int* decoder_result, int n_new_items, const float* emb_table,
+                      const float* pos_table, float** page_table, const float* wk, const float* wq,
+                      const float* wv, float* q_output, float* attention_result, int n_batch,
+                      int n_sequence, int emb_dim, int n_vocab, int n_forward_rounds);
+
+/* ---- dense (non-paged) stages: BASELINE config C1 ------------------------------------------ */
+/* replaces launch_inference_optimized_encoder_kernel (encoder.h:16-19; encoder.cu:56-92) */
+int mli_dense_encoder(mli_ctx* ctx, const float* emb_table, const float* pos_table, const int* inp,
+                      float* inp_embedding, const int* lengths, const int* new_item_indices,
+                      int n_batch, int n_sequence, int emb_dim, int n_new_items);
+
+/* replaces inference_self_attention (include/kernels/self_attention_inference_optimized.h:37-47;
+ * self_attention_inference_optimized.cu:27-383).  kt_cache is TRANSPOSED [B,d_out,S], v_cache
+ * [B,S,d_out].  qkt_output[B,S] receives the softmax probabilities (zeros past L) as in the
+ * reference; may be NULL. */
+int mli_self_attention(mli_ctx* ctx, const float* inp_embedding, const int* lengths, const float* wk,
+                       const float* wq, const float* wv, const int* new_batch_idx, float* kt_cache,
+                       float* v_cache, float* q_output, float* qkt_output, float* attention_result,
+                       int n_new_items, int n_batch, int n_sequence, int input_dim, int output_dim);
+
+/* replaces launch_decoder (decoder.h:19-24; decoder.cu:25-112) */
+int mli_dense_decoder(mli_ctx* ctx, const float* batch_result, const float* emb_table,
+                      float* emb_score, const float* pos_table, float* inp_embedding, int* lengths,
+                      int* decoder_result, int n_batch, int n_vocab, int n_sequence, int emb_dim);
+
+/* replaces InferenceModel::forward (inference_model.h:8-30; inference_model.cpp:14-39) */
+int mli_dense_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new_item_indices,
+                      int* decoder_result, int n_new_items, const float* emb_table,
+                      const float* pos_table, const float* wk, const float* wq, const float* wv,
+                      float* inp_embedding, float* kt_cache, float* v_cache, float* q_output,
+                      float* attention_result, int n_batch, int n_sequence, int emb_dim, int n_vocab);
+
+/* ---- on-device continuous-batching engine --------------------------------------------------- */
+/* replaces start_paged_attention_inference_engine / ..._cublas_... (include/inferencer.h:23-32;
+ * src/inferencer.cpp:43-133) together with the host scheduler it drives: paged insert_new_items,
+ * allocate_or_free_memory_blocks_if_needed, process_decoder_result, MemoryBlockManager and
+ * PagedAttentionsManager (src/paged_item_storage.cpp:14-203, src/item_storage.cpp:97-139).
+ * Requests, the page free list, the page table and all admission / retirement / growth /
+ * pre-emption decisions live on the device; the host only launches a CUDA graph per step and
+ * polls a pinned completion word. */
+typedef struct {
+    int n_batch, n_sequence, emb_dim, n_vocab;
+    int n_blocks;          /* KV pages in the pool */
+    int n_forward_rounds;  /* 1..16 */
+    int compat_stale_lengths; /* 1 = reproduce the reference's stale-lengths behaviour
+                                 (paged_item_storage.cpp:73-75,:114-118) so
+                                 token lists match the reference engine; 0 = corrected */
+    int max_requests;      /* capacity of the device request table */
+    float* page_pool;      /* optional caller-owned slab of n_blocks*16*3*d floats (e.g. the
+                              reference's MemoryBlockManager slab); NULL = engine allocates */
+} mli_engine_cfg;
+
+typedef struct {
+    long long steps;            /* engine iterations (each = n_forward_rounds decode rounds) */
+    long long generated_tokens; /* tokens appended to requests */
+    long long preemptions;
+    long long admitted;
+    int n_finished;
+    float gpu_ms;               /* device time of the last mli_engine_run (CUDA events) */
+    float attn_ms;              /* device time spent in the fused decode-attention kernels, only
+                                   when profiling was requested (else 0) */
+    double attn_bytes;          /* algorithmic bytes of those launches (SURVEY 8d ATTN_BYTES) */
+    long long attn_launches;
+} mli_engine_stats;
+
+typedef struct mli_engine mli_engine;
+
+int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_table,
+                      const float* pos_table, const float* wk, const float* wq, const float* wv,
+                      mli_engine** out);
+int mli_engine_destroy(mli_engine* e);
+/* upload requests; prompt_offsets[n_req+1] / prompt_tokens are HOST pointers (is_device = 0) or
+ * DEVICE pointers (is_device = 1, used by bench.py's device-resident leg).  Resets the engine. */
+int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
+                      int is_device);
+/* run to completion (max_steps <= 0) or for at most max_steps iterations.
+ * profile_attention != 0 brackets every fused-attention launch with CUDA events (no graph). */
+int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention);
+/* download finished requests in finish order (HOST buffers): ids[n_req], offsets[n_req+1],
+ * tokens[n_req * n_sequence] (prompt + generated) */
+int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, int* finished_tokens,
+                       int* n_finished);
+int mli_engine_get_stats(mli_engine* e, mli_engine_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,159 @@
+// common.cuh -- shared device/host helpers for the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "mli_b200.h"
+
+namespace mli {
+
+constexpr int kPage = MLI_PAGE_BLOCK_SIZE;  // positions per KV page (reference include/constants.h:12)
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* file, int line);
+void count_launch(int n = 1);
+
+#define MLI_CUDA(expr)                                              \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return mli::cuda_fail(_e, __FILE__, __LINE__); \
+    } while (0)
+
+#define MLI_LAUNCH_CHECK()                                          \
+    do {                                                            \
+        cudaError_t _e = cudaGetLastError();                        \
+        if (_e != cudaSuccess) return mli::cuda_fail(_e, __FILE__, __LINE__); \
+        mli::count_launch();                                        \
+    } while (0)
+
+#define MLI_REQUIRE(cond, msg)                                      \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            mli::set_error(std::string("argument error: ") + (msg)); \
+            return MLI_ERR_ARG;                                     \
+        }                                                           \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- page addressing (reference include/utils.h:32-60) -------------------------------------
+// element (row r, position j, sub-row off, column c) =
+//   page_table[r*W + j/16][(j%16)*3*d + off*d + c]
+__device__ __forceinline__ float* page_row_ptr(float* page, int j, int d, int off) {
+    return page + (size_t)(j & (kPage - 1)) * 3 * d + (size_t)off * d;
+}
+
+// ---- PTX wrappers: mbarrier + bulk async copy (TMA, non-tensor form) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+    // make barrier initialisation visible to the async proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace mli
+
+// ---- context (shared by all translation units) ---------------------------------------------
+namespace mli {
+enum WsSlot {
+    WS_ATTN_META = 0,  // item lists / per-row prefix for the fused attention
+    WS_ATTN_PART,      // split-KV partial accumulators
+    WS_TILES,          // M-tile lists for prefill / encoder
+    WS_LOGITS,         // [B,V] logits when the caller does not want them
+    WS_QOUT,           // q_output when the caller passes NULL
+    WS_ATTN_OUT,       // attention_result when the caller passes NULL
+    WS_QKT,            // dense-path score scratch
+    WS_GEMM_A,         // tcgen05 path: dense activation staging
+    WS_GEMM_C,         // tcgen05 path: dense output staging
+    WS_NUM_SLOTS
+};
+}  // namespace mli
+
+struct mli_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    int gemm_mode = 1;          // MLI_OPT_GEMM_MODE
+    int tc_available = 0;       // tcgen05 GEMM path usable on this device
+    int attn_chunk_pages = 0;   // 0 = auto
+    int attn_ctas_per_sm = 0;   // 0 = auto
+    void* ws[mli::WS_NUM_SLOTS] = {};
+    size_t ws_bytes[mli::WS_NUM_SLOTS] = {};
+    bool ws_frozen = false;     // set while a CUDA graph that captured ws pointers is alive
+    // when set, the fused decode-attention main kernel is bracketed by these events (profiling)
+    cudaEvent_t attn_ev_start = nullptr, attn_ev_stop = nullptr;
+};
+
+namespace mli {
+// device buffer of at least `bytes` for `slot` (grows with a synchronous re-allocation; growing
+// while frozen is an error because captured graphs hold the old pointer)
+int ws_get(mli_ctx* ctx, int slot, size_t bytes, void** out);
+}  // namespace mli

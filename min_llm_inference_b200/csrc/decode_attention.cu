@@ -1,0 +1,542 @@
+// decode_attention.cu -- fused, length-aware, split-KV paged decode attention for sm_100a.
+//
+// Replaces the reference's three-kernel chain
+//   qkt_paged_attention            (src/kernels/paged_attention.cu:208-263)
+//   softmax_in_place_with_lengths  (src/kernels/self_attention_inference_optimized.cu:191-242)
+//   softmax_v_paged_attention      (src/kernels/paged_attention.cu:287-326)
+// and its [B,S] score round-trips with one pass over K and V.
+//
+// Design (HBM-bound; SURVEY 8d: ATTN_BYTES = sum_r 8*d*L_r + 8*d + 8*ceil(L_r/16) + 4):
+//   * work item = (row, chunk of CH pages); a tiny prep kernel lists the items from the device
+//     lengths, persistent CTAs (a multiple of the SM count) walk the list round-robin;
+//   * one producer warp streams K|V rows (they are adjacent inside a page: [inp|K|V] per
+//     position, so one 8*d-byte bulk copy per position) into a shared-memory ring with
+//     cp.async.bulk + mbarrier complete_tx (TMA, non-tensor form -- page tables hold raw pointers,
+//     so a tensor map cannot follow them); page pointers of the chunk are fetched once per item
+//     and handed round by warp shuffle;
+//   * eight consumer warps: each thread owns float4 columns of d; q.K partial dots are reduced by
+//     warp shuffle + a small shared array; online softmax (running max / sum) in fp32;
+//     P.V accumulates in registers; K and V are each read exactly once from HBM;
+//   * split partials (m, l, acc[d]) are merged by a small combine kernel which also zero-fills
+//     empty rows and (optionally) materialises the reference's [B,S] probabilities.
+// Scale is dot / sqrtf(d) (a division, paged_attention.cu:261) and the exponent is expf, as in
+// the reference.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace mli {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kAttnThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kMaxStages = 8;
+
+// ---------------------------------------------------------------------------------------------
+// prep: list the work items.  One CTA; rows are scanned in blocks of blockDim.x.
+//   row_first[r]   first item of row r (exclusive prefix of chunk counts), row_first[B] = total
+//   item_row/item_chunk[i]
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chunk_pos,
+                                 int* __restrict__ row_first, int* __restrict__ item_row,
+                                 int* __restrict__ item_chunk) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += blockDim.x) {
+        int r = base + tid;
+        int L = (r < B) ? lengths[r] : 0;
+        int n = (L + chunk_pos - 1) / chunk_pos;
+        // inclusive warp scan
+        int v = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = (lane < nwarps) ? warp_tot[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;  // inclusive totals of warps
+        }
+        __syncthreads();
+        int carry = carry_s;
+        int first = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + v - n;
+        if (r < B) {
+            row_first[r] = first;
+            for (int c = 0; c < n; ++c) {
+                item_row[first + c] = r;
+                item_chunk[first + c] = c;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry_s = carry + warp_tot[nwarps - 1];
+        __syncthreads();
+    }
+    if (tid == 0) row_first[B] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+template <int NC, int G>
+__global__ void __launch_bounds__(kAttnThreads)
+decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ page_table,
+                        const int* __restrict__ lengths, const int* __restrict__ row_first,
+                        const int* __restrict__ item_row, const int* __restrict__ item_chunk,
+                        float* __restrict__ out, float* __restrict__ part_acc,
+                        float* __restrict__ part_ml, float* __restrict__ scores_out, int B, int S,
+                        int d, int chunk_pages, int nstage) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = S / kPage;
+    const int d4 = d >> 2;
+    const int row_floats = 2 * d;            // K row followed by V row
+    const int stage_floats = G * row_floats;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_floats);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    float* red = reinterpret_cast<float*>(empty_bar + kMaxStages);  // [2][kConsumerWarps][G]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n_items = row_first[B];
+    const int chunk_pos = chunk_pages * kPage;
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer warp =====================
+        uint32_t it = 0;  // running stage counter across items
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int r = item_row[item];
+            const int c = item_chunk[item];
+            const int L = lengths[r];
+            const int p0 = c * chunk_pos;
+            const int p1 = min(L, p0 + chunk_pos);
+            // page pointers of this chunk: lane i holds page (c*CH + i)
+            const int npages = (p1 - p0 + kPage - 1) / kPage;
+            const float* my_page = nullptr;
+            if (lane < npages) my_page = page_table[(size_t)r * W + (size_t)c * chunk_pages + lane];
+            for (int pos = p0; pos < p1; pos += G, ++it) {
+                const int stage = it % nstage;
+                const uint32_t parity = (it / nstage) & 1u;
+                const int nvalid = min(G, p1 - pos);
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[stage], parity ^ 1u);
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)nvalid * row_floats * 4u);
+                }
+                __syncwarp();
+                // lane g copies position pos+g (K|V rows are contiguous: 8*d bytes)
+                const int j = pos + (lane < G ? lane : 0);
+                const int pg = (j - p0) / kPage;
+                const float* page = reinterpret_cast<const float*>(
+                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_page), pg));
+                if (lane < nvalid) {
+                    const float* src = page + (size_t)(j & (kPage - 1)) * 3 * d + d;
+                    bulk_g2s(ring + (size_t)stage * stage_floats + (size_t)lane * row_floats, src,
+                             (uint32_t)row_floats * 4u, &full_bar[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const float inv_dummy = 0.f;
+    (void)inv_dummy;
+    const float sqrt_d = sqrtf((float)d);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int r = item_row[item];
+        const int c = item_chunk[item];
+        const int L = lengths[r];
+        const int p0 = c * chunk_pos;
+        const int p1 = min(L, p0 + chunk_pos);
+        const int nchunks = (L + chunk_pos - 1) / chunk_pos;
+
+        float4 qv[NC];
+        float4 acc[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int col = tid + i * kConsumerThreads;
+            qv[i] = (col < d4) ? reinterpret_cast<const float4*>(q + (size_t)r * d)[col]
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float m_run = -INFINITY, l_run = 0.f;
+
+        for (int pos = p0; pos < p1; pos += G, ++it) {
+            const int stage = it % nstage;
+            const uint32_t parity = (it / nstage) & 1u;
+            const int nvalid = min(G, p1 - pos);
+            const float* sbase = ring + (size_t)stage * stage_floats;
+            float* red_buf = red + (size_t)(it & 1u) * kConsumerWarps * G;
+            mbar_wait(&full_bar[stage], parity);
+
+            // ---- phase A: partial q.K over this thread's columns, warp reduce ----
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float s = 0.f;
+                if (g < nvalid) {
+                    const float4* krow = reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int col = tid + i * kConsumerThreads;
+                        if (col < d4) {
+                            const float4 k = krow[col];
+                            s = fmaf(qv[i].x, k.x, s);
+                            s = fmaf(qv[i].y, k.y, s);
+                            s = fmaf(qv[i].z, k.z, s);
+                            s = fmaf(qv[i].w, k.w, s);
+                        }
+                    }
+                }
+                s = warp_sum(s);
+                if (lane == 0) red_buf[warp * G + g] = s;
+            }
+            named_bar_sync(1, kConsumerThreads);
+
+            // ---- every thread rebuilds the G scores identically ----
+            float sc[G];
+            float m_new = m_run;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < kConsumerWarps; ++w) s += red_buf[w * G + g];
+                s = s / sqrt_d;
+                sc[g] = s;
+                if (g < nvalid) m_new = fmaxf(m_new, s);
+            }
+            if (scores_out != nullptr) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    if (tid == g && g < nvalid) scores_out[(size_t)r * S + pos + g] = sc[g];
+            }
+            const float corr = expf(m_run - m_new);  // exp(-inf) = 0 on the first stage
+            l_run *= corr;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr;
+            }
+            // ---- phase B: P.V ----
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (g < nvalid) {
+                    const float p = expf(sc[g] - m_new);
+                    l_run += p;
+                    const float4* vrow =
+                        reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats + d);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int col = tid + i * kConsumerThreads;
+                        if (col < d4) {
+                            const float4 v = vrow[col];
+                            acc[i].x = fmaf(p, v.x, acc[i].x);
+                            acc[i].y = fmaf(p, v.y, acc[i].y);
+                            acc[i].z = fmaf(p, v.z, acc[i].z);
+                            acc[i].w = fmaf(p, v.w, acc[i].w);
+                        }
+                    }
+                }
+            }
+            m_run = m_new;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        }
+
+        // ---- item epilogue ----
+        if (tid == 0) {
+            part_ml[2 * (size_t)item] = m_run;
+            part_ml[2 * (size_t)item + 1] = l_run;
+        }
+        if (nchunks == 1) {
+            const float norm = 1.f / l_run;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int col = tid + i * kConsumerThreads;
+                if (col < d4)
+                    reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(
+                        acc[i].x * norm, acc[i].y * norm, acc[i].z * norm, acc[i].w * norm);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int col = tid + i * kConsumerThreads;
+                if (col < d4) reinterpret_cast<float4*>(part_acc + (size_t)item * d)[col] = acc[i];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// combine: one CTA per row.  nchunks == 0 -> zeros (the reference stores result = 0 for empty
+// rows, paged_attention.cu:289,:323); nchunks == 1 -> already final; else merge partials.
+// Optionally turns the raw scores in scores_out into the reference's probabilities
+// expf(s - max) * (1.f / sum), zeros past L (self_attention_inference_optimized.cu:226-241).
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_combine_kernel(const int* __restrict__ lengths,
+                                    const int* __restrict__ row_first,
+                                    const float* __restrict__ part_acc,
+                                    const float* __restrict__ part_ml, float* __restrict__ out,
+                                    float* __restrict__ scores_out, int S, int d) {
+    const int r = blockIdx.x;
+    const int first = row_first[r];
+    const int n = row_first[r + 1] - first;
+    const int d4 = d >> 2;
+    const int L = lengths[r];
+    float M = -INFINITY, Lsum = 0.f;
+    if (n > 0) {
+        for (int i = 0; i < n; ++i) M = fmaxf(M, part_ml[2 * (size_t)(first + i)]);
+        for (int i = 0; i < n; ++i)
+            Lsum += part_ml[2 * (size_t)(first + i) + 1] * expf(part_ml[2 * (size_t)(first + i)] - M);
+    }
+    if (n == 0) {
+        for (int col = threadIdx.x; col < d4; col += blockDim.x)
+            reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (n > 1) {
+        const float norm = 1.f / Lsum;
+        for (int col = threadIdx.x; col < d4; col += blockDim.x) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < n; ++i) {
+                const float w = expf(part_ml[2 * (size_t)(first + i)] - M);
+                const float4 p = reinterpret_cast<const float4*>(part_acc + (size_t)(first + i) * d)[col];
+                a.x = fmaf(w, p.x, a.x); a.y = fmaf(w, p.y, a.y);
+                a.z = fmaf(w, p.z, a.z); a.w = fmaf(w, p.w, a.w);
+            }
+            reinterpret_cast<float4*>(out + (size_t)r * d)[col] =
+                make_float4(a.x * norm, a.y * norm, a.z * norm, a.w * norm);
+        }
+    }
+    if (scores_out != nullptr) {
+        const float norm = (n > 0) ? 1.f / Lsum : 0.f;
+        float* row = scores_out + (size_t)r * S;
+        for (int j = threadIdx.x; j < S; j += blockDim.x)
+            row[j] = (j < L) ? expf(row[j] - M) * norm : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+struct AttnPlan {
+    int NC, G, nstage, chunk_pages, grid;
+    size_t smem;
+    int max_items;
+};
+
+static int plan_attention(mli_ctx* ctx, int B, int S, int d, AttnPlan* p) {
+    const int W = S / kPage;
+    if (d > 4096) {
+        set_error("decode attention: emb_dim > 4096 is not supported by this build");
+        return MLI_ERR_UNSUPPORTED;
+    }
+    p->NC = (d + 1023) / 1024;
+    if (p->NC == 3) p->NC = 4;
+    int G = 1;
+    while (G < 16 && 2 * G * d <= 4096) G <<= 1;  // G*d <= 4096 floats of K per stage
+    p->G = G;
+    const size_t stage_bytes = (size_t)G * 2 * d * 4;
+    int ctas = ctx->attn_ctas_per_sm > 0 ? ctx->attn_ctas_per_sm : 2;
+    const size_t budget = (ctas >= 2) ? 100 * 1024 : 200 * 1024;
+    int nstage = (int)(budget / stage_bytes);
+    if (nstage < 2) nstage = 2;
+    if (nstage > kMaxStages) nstage = kMaxStages;
+    p->nstage = nstage;
+    p->smem = nstage * stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
+              2 * kConsumerWarps * G * sizeof(float) + 128;
+    int ch = ctx->attn_chunk_pages;
+    if (ch <= 0) {
+        // aim for a few items per persistent CTA without making items tiny
+        long long pages = (long long)B * W;
+        ch = (int)((pages + (long long)ctx->num_sms * 16 - 1) / ((long long)ctx->num_sms * 16));
+        if (ch < 2) ch = 2;
+        if (ch > 16) ch = 16;
+    }
+    if (ch > 32) ch = 32;
+    if (ch > W) ch = W;
+    p->chunk_pages = ch;
+    p->max_items = B * ceil_div(W, ch);
+    p->grid = ctx->num_sms * ctas;
+    if (p->grid > p->max_items) p->grid = p->max_items;
+    if (p->grid < 1) p->grid = 1;
+    return 0;
+}
+
+size_t attention_meta_bytes(int B, int max_items) {
+    return sizeof(int) * ((size_t)B + 1 + 2 * (size_t)max_items + 8);
+}
+
+template <int NC, int G>
+static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* const* page_table,
+                       const int* lengths, const int* row_first, const int* item_row,
+                       const int* item_chunk, float* out, float* part_acc, float* part_ml,
+                       float* scores_out, int B, int S, int d) {
+    auto kern = decode_attention_kernel<NC, G>;
+    static size_t configured = 0;  // per instantiation
+    if (configured < p.smem) {
+        MLI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        configured = p.smem;
+    }
+    if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
+    kern<<<p.grid, kAttnThreads, p.smem, ctx->stream>>>(q, page_table, lengths, row_first, item_row,
+                                                         item_chunk, out, part_acc, part_ml,
+                                                         scores_out, B, S, d, p.chunk_pages,
+                                                         p.nstage);
+    MLI_LAUNCH_CHECK();
+    if (ctx->attn_ev_stop) MLI_CUDA(cudaEventRecord(ctx->attn_ev_stop, ctx->stream));
+    return 0;
+}
+
+int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_table,
+                                  const int* lengths, float* out, float* softmax_out, int B, int S,
+                                  int d) {
+    AttnPlan p;
+    int rc = plan_attention(ctx, B, S, d, &p);
+    if (rc) return rc;
+    void* meta = nullptr;
+    void* part = nullptr;
+    rc = ws_get(ctx, WS_ATTN_META, attention_meta_bytes(B, p.max_items), &meta);
+    if (rc) return rc;
+    rc = ws_get(ctx, WS_ATTN_PART, sizeof(float) * ((size_t)p.max_items * (d + 2) + 8), &part);
+    if (rc) return rc;
+    int* row_first = reinterpret_cast<int*>(meta);
+    int* item_row = row_first + B + 1;
+    int* item_chunk = item_row + p.max_items;
+    float* part_ml = reinterpret_cast<float*>(part);
+    float* part_acc = part_ml + 2 * (size_t)p.max_items;
+    // keep part_acc 16-byte aligned
+    part_acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(part_acc) + 15) & ~(uintptr_t)15);
+
+    attn_prep_kernel<<<1, 1024, 0, ctx->stream>>>(lengths, B, p.chunk_pages * kPage, row_first,
+                                                   item_row, item_chunk);
+    MLI_LAUNCH_CHECK();
+
+#define MLI_ATTN_CASE(NC_, G_)                                                                   \
+    if (p.NC == NC_ && p.G == G_)                                                                \
+        rc = launch_main<NC_, G_>(p, ctx, q, page_table, lengths, row_first, item_row, item_chunk, \
+                                  out, part_acc, part_ml, softmax_out, B, S, d);                 \
+    else
+    MLI_ATTN_CASE(1, 16)
+    MLI_ATTN_CASE(1, 8)
+    MLI_ATTN_CASE(1, 4)
+    MLI_ATTN_CASE(1, 2)
+    MLI_ATTN_CASE(2, 2)
+    MLI_ATTN_CASE(2, 1)
+    MLI_ATTN_CASE(4, 1) {
+        set_error("decode attention: no kernel instantiation for this emb_dim");
+        return MLI_ERR_UNSUPPORTED;
+    }
+#undef MLI_ATTN_CASE
+    if (rc) return rc;
+
+    attn_combine_kernel<<<B, 256, 0, ctx->stream>>>(lengths, row_first, part_acc, part_ml, out,
+                                                    softmax_out, S, d);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense (non-paged) decode attention for BASELINE config C1: kt_cache is TRANSPOSED [B,d,S]
+// (self_attention_inference_optimized.cu:150-279).  One CTA per row; scores are accumulated
+// c-ascending per position and P.V j-ascending per column, i.e. in the reference's own order
+// (qkt :174-176, softmax_v :268-270), so only expf / the softmax sums differ from it.  C1 is
+// L2-resident and launch-bound, so this kernel is written for fidelity, not bandwidth.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dense_attention_kernel(const float* __restrict__ q, const float* __restrict__ kt,
+                       const float* __restrict__ v, const int* __restrict__ lengths,
+                       float* __restrict__ out, float* __restrict__ softmax_out, int S, int d) {
+    extern __shared__ float dsm[];
+    float* p = dsm;          // [S]
+    float* qs = dsm + S;     // [d]
+    __shared__ float red[32];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = lengths[r];
+    for (int c = tid; c < d; c += 256) qs[c] = q[(size_t)r * d + c];
+    __syncthreads();
+    const float sqrt_d = sqrtf((float)d);
+    const float* ktr = kt + (size_t)r * d * S;
+    float lmax = -FLT_MAX;
+    for (int j = tid; j < L; j += 256) {
+        float s = 0.f;
+        for (int c = 0; c < d; ++c) s = fmaf(qs[c], ktr[(size_t)c * S + j], s);
+        s = s / sqrt_d;
+        p[j] = s;
+        lmax = fmaxf(lmax, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if (lane == 0) red[warp] = lmax;
+    __syncthreads();
+    float gmax = -FLT_MAX;
+    for (int w = 0; w < 8; ++w) gmax = fmaxf(gmax, red[w]);
+    __syncthreads();
+    float lsum = 0.f;
+    for (int j = tid; j < L; j += 256) lsum += expf(p[j] - gmax);
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[warp] = lsum;
+    __syncthreads();
+    float gsum = 0.f;
+    for (int w = 0; w < 8; ++w) gsum += red[w];
+    const float norm = 1.f / gsum;
+    for (int j = tid; j < L; j += 256) p[j] = expf(p[j] - gmax) * norm;
+    __syncthreads();
+    const float* vr = v + (size_t)r * S * d;
+    for (int c = tid; c < d; c += 256) {
+        float a = 0.f;
+        for (int j = 0; j < L; ++j) a = fmaf(p[j], vr[(size_t)j * d + c], a);
+        out[(size_t)r * d + c] = a;
+    }
+    if (softmax_out != nullptr)
+        for (int j = tid; j < S; j += 256) softmax_out[(size_t)r * S + j] = (j < L) ? p[j] : 0.f;
+}
+
+int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_cache,
+                                  const float* v_cache, const int* lengths, float* out,
+                                  float* softmax_out, int B, int S, int d) {
+    const size_t smem = sizeof(float) * ((size_t)S + d);
+    if (smem > 200 * 1024) {
+        set_error("dense attention: n_sequence + emb_dim too large for shared memory");
+        return MLI_ERR_UNSUPPORTED;
+    }
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        MLI_CUDA(cudaFuncSetAttribute(dense_attention_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dense_attention_kernel<<<B, 256, smem, ctx->stream>>>(q, kt_cache, v_cache, lengths, out,
+                                                          softmax_out, S, d);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+// algorithmic bytes of one decode-attention launch, from host-side lengths
+double attention_algorithmic_bytes(const int* lengths_host, int B, int d) {
+    double total = 0;
+    for (int r = 0; r < B; ++r) {
+        int L = lengths_host[r];
+        if (L > 0) total += 8.0 * d * L + 8.0 * d + 8.0 * ((L + kPage - 1) / kPage) + 4.0;
+    }
+    return total;
+}
+
+}  // namespace mli

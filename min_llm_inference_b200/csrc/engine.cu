@@ -1,0 +1,805 @@
+// engine.cu -- on-device continuous-batching engine (mli_engine_*).
+//
+// Replaces the host loop start_paged_attention_inference_engine (src/inferencer.cpp:43-85) and the
+// host scheduler it drives:
+//   process_decoder_result                    src/item_storage.cpp:97-139
+//   allocate_or_free_memory_blocks_if_needed  src/paged_item_storage.cpp:14-60
+//   paged insert_new_items                    src/paged_item_storage.cpp:62-122
+//   MemoryBlockManager / PagedAttentionsManager  src/paged_item_storage.cpp:125-203
+// The request table (prompt + generated tokens), the request deque, the page free list, the page
+// table, the used-row list and every admission / retirement / growth / pre-emption decision live
+// in HBM and are advanced by ONE scheduler kernel per iteration; the model kernels that follow read
+// their work (lengths, new rows, tile list) from device memory.  A whole iteration is captured in a
+// CUDA graph; the host launches graphs a few steps ahead and polls a mapped, pinned "done" word --
+// the reference's per-step cudaMemcpy round trips (1 D2H + up to 4 H2D) are gone.
+//
+// Decision parity with the reference (what decides tokens): admission scans rows in index order and
+// takes the queue head while free >= max(4, ceil((len+R)/16)) (Q6); finished rows are retired in
+// row order; growth walks the used list in admission order, one page per row, and pre-empts the
+// list TAIL back to the FRONT of the queue when the pool is empty (Q3); compat_stale_lengths = 1
+// additionally replays quirk Q1 (every in-flight row's device length snaps back to its admission
+// length whenever any row is unoccupied).  What is NOT replayed is the physical order of the free
+// list (pages are returned in table order), which only changes which page a row gets, never a token.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <vector>
+
+namespace mli {
+
+struct SchedVars {
+    int q_head, q_count, q_cap;
+    int f_head, f_count;
+    int n_used, n_fin, n_new;
+    int iter, done, error, n_req;
+    long long steps, generated, preemptions, admitted;
+};
+
+struct SchedArgs {
+    SchedVars* v;
+    int* req_tok;     // [max_req][S]
+    int* req_cnt;     // [max_req]
+    int* queue;       // [q_cap] ring of request ids
+    int* fin_ids;     // [max_req]
+    int* row_req;     // [B]
+    int* lengths;     // [B] device lengths (what the kernels read)
+    int* len_shadow;  // [B] the reference's lengths_host (admission length or 0)
+    int* used;        // [B] used-row list in admission order
+    int* npages;      // [B]
+    float** page_table;  // [B][W]
+    float** free_ring;   // [n_blocks]
+    int* dec;         // [B][R]
+    int* new_idx;     // [B]
+    int* flag_fin;    // [B] scratch
+    int* flag_free;   // [B] scratch
+    int* need_list;   // [B] scratch
+    int* free_rows;   // [B] scratch
+    int* occ;         // [B] scratch
+    volatile int* done_host;  // mapped pinned
+    int B, S, W, R, n_blocks, compat;
+};
+
+constexpr int kSchedThreads = 1024;
+
+// exclusive block scan; every thread must call it.  total = sum over the block.
+__device__ int block_scan_excl(int v, int* total, int* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < nwarps) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int res = x - v + (warp > 0 ? s_warp[warp - 1] : 0);
+    *total = s_warp[nwarps - 1];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry[4];
+    const int tid = threadIdx.x, T = blockDim.x;
+    SchedVars* v = a.v;
+    const int B = a.B, S = a.S, W = a.W, R = a.R;
+
+    if (v->done) {
+        __syncthreads();
+        if (tid == 0) v->n_new = 0;
+        return;
+    }
+    const bool first = (v->iter == 0);
+    __syncthreads();
+
+    if (!first) {
+        // ================= phase 1: process_decoder_result (item_storage.cpp:97-139) =================
+        int local_gen = 0;
+        for (int r = tid; r < B; r += T) {
+            bool empty = false, finished = false;
+            const int id = a.row_req[r];
+            for (int j = 0; j < R; ++j) {
+                const int t = a.dec[(size_t)r * R + j];
+                if (t == MLI_EMPTY_ROW_TOKEN_ID) {
+                    empty = true;
+                } else if (id < 0) {
+                    v->error = 1;  // token for a row that is not processing
+                    empty = true;
+                } else {
+                    int c = a.req_cnt[id];
+                    if (c < S) a.req_tok[(size_t)id * S + c] = t;
+                    c += 1;
+                    a.req_cnt[id] = c;
+                    ++local_gen;
+                    if (c >= S || t == MLI_EOF_TOKEN_ID) finished = true;
+                }
+                if (finished || empty) break;
+            }
+            a.flag_fin[r] = finished ? 1 : 0;
+            a.flag_free[r] = (finished || empty) ? 1 : 0;
+        }
+        if (local_gen) atomicAdd(reinterpret_cast<unsigned long long*>(&v->generated),
+                                 (unsigned long long)local_gen);
+        __syncthreads();
+        // finished requests are appended in row order (:118-131)
+        if (tid == 0) s_carry[0] = 0;
+        __syncthreads();
+        for (int base = 0; base < B; base += T) {
+            const int r = base + tid;
+            const int f = (r < B) ? a.flag_fin[r] : 0;
+            int tot;
+            const int pos = block_scan_excl(f, &tot, s_warp);
+            if (f) {
+                const int id = a.row_req[r];
+                if (a.req_cnt[id] > S) a.req_cnt[id] = S;
+                a.fin_ids[v->n_fin + s_carry[0] + pos] = id;
+                a.row_req[r] = -1;
+            }
+            __syncthreads();
+            if (tid == 0) s_carry[0] += tot;
+            __syncthreads();
+        }
+        if (tid == 0) v->n_fin += s_carry[0];
+        __syncthreads();
+
+        // ================= phase 2: free rows in finished_indices (paged_item_storage.cpp:20-32) =====
+        {
+            const int n_used = v->n_used;
+            const int f_tail0 = v->f_head + v->f_count;
+            if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+            __syncthreads();
+            for (int base = 0; base < n_used; base += T) {
+                const int i = base + tid;
+                int row = -1, rel = 0, keep = 0, np = 0;
+                if (i < n_used) {
+                    row = a.used[i];
+                    rel = a.flag_free[row];
+                    keep = !rel;
+                    np = rel ? a.npages[row] : 0;
+                }
+                int totp, totk;
+                const int ppos = block_scan_excl(np, &totp, s_warp);
+                const int kpos = block_scan_excl(keep, &totk, s_warp);
+                // all reads of used[] in this chunk are done (scan contains barriers)
+                if (rel) {
+                    const int o = f_tail0 + s_carry[0] + ppos;
+                    for (int t = 0; t < np; ++t)
+                        a.free_ring[(o + t) % a.n_blocks] = a.page_table[(size_t)row * W + t];
+                    a.npages[row] = 0;
+                }
+                if (keep) a.used[s_carry[1] + kpos] = row;
+                __syncthreads();
+                if (tid == 0) { s_carry[0] += totp; s_carry[1] += totk; }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                v->f_count += s_carry[0];
+                v->n_used = s_carry[1];
+            }
+            __syncthreads();
+        }
+
+        // ================= phase 3: grow / pre-empt (paged_item_storage.cpp:36-59) ===================
+        {
+            const int n_used = v->n_used;
+            if (tid == 0) s_carry[0] = 0;
+            __syncthreads();
+            for (int base = 0; base < n_used; base += T) {
+                const int i = base + tid;
+                int need = 0;
+                if (i < n_used) {
+                    const int row = a.used[i];
+                    const int id = a.row_req[row];
+                    need = (a.req_cnt[id] + R > a.npages[row] * kPage) ? 1 : 0;
+                }
+                int tot;
+                const int pos = block_scan_excl(need, &tot, s_warp);
+                if (need) a.need_list[s_carry[0] + pos] = i;
+                __syncthreads();
+                if (tid == 0) s_carry[0] += tot;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const int m = s_carry[0];
+                int n = n_used, F = v->f_count, fh = v->f_head, qh = v->q_head, qc = v->q_count;
+                long long pre = 0;
+                auto preempt = [&](int row) {
+                    // move_to_new: front of the queue, keeping generated tokens (item_storage.cpp:75-79)
+                    qh = (qh - 1 + v->q_cap) % v->q_cap;
+                    a.queue[qh] = a.row_req[row];
+                    ++qc;
+                    a.row_req[row] = -1;
+                    const int np = a.npages[row];
+                    for (int t = 0; t < np; ++t)
+                        a.free_ring[(fh + F + t) % a.n_blocks] = a.page_table[(size_t)row * W + t];
+                    F += np;
+                    a.npages[row] = 0;
+                    ++pre;
+                };
+                for (int k = 0; k < m; ++k) {
+                    const int i = a.need_list[k];
+                    if (i >= n) break;  // already pre-empted as a tail
+                    const int row = a.used[i];
+                    for (;;) {
+                        if (F > 0) {
+                            // allocate_memory_block (:196-203): new page at table index size-1
+                            const int np = a.npages[row];
+                            if (np < W) {
+                                a.page_table[(size_t)row * W + np] = a.free_ring[fh];
+                                fh = (fh + 1) % a.n_blocks;
+                                --F;
+                                a.npages[row] = np + 1;
+                            }
+                            break;
+                        } else if (i == n - 1) {
+                            preempt(row);
+                            --n;
+                            break;
+                        } else {
+                            preempt(a.used[n - 1]);
+                            --n;
+                        }
+                    }
+                }
+                v->n_used = n;
+                v->f_count = F;
+                v->f_head = fh;
+                v->q_head = qh;
+                v->q_count = qc;
+                v->preemptions += pre;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ================= phase 4: insert_new_items (paged_item_storage.cpp:62-122) =====================
+    {
+        const int n_used = v->n_used;
+        for (int r = tid; r < B; r += T) a.occ[r] = 0;
+        __syncthreads();
+        for (int i = tid; i < n_used; i += T) a.occ[a.used[i]] = 1;
+        __syncthreads();
+        // unoccupied rows in index order
+        if (tid == 0) s_carry[0] = 0;
+        __syncthreads();
+        for (int base = 0; base < B; base += T) {
+            const int r = base + tid;
+            const int fr = (r < B && !a.occ[r]) ? 1 : 0;
+            int tot;
+            const int pos = block_scan_excl(fr, &tot, s_warp);
+            if (fr) a.free_rows[s_carry[0] + pos] = r;
+            __syncthreads();
+            if (tid == 0) s_carry[0] += tot;
+            __syncthreads();
+        }
+        const int n_free_rows = s_carry[0];
+        const int F = v->f_count, fh = v->f_head, qh = v->q_head, qc = v->q_count;
+        const int n_cand = min(n_free_rows, qc);
+        __syncthreads();
+        // candidate j takes queue item j; admitted iff cumulative page need <= F (a prefix)
+        if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+        __syncthreads();
+        for (int base = 0; base < n_cand; base += T) {
+            const int j = base + tid;
+            int id = -1, len = 0, need = 0;
+            if (j < n_cand) {
+                id = a.queue[(qh + j) % v->q_cap];
+                len = a.req_cnt[id];
+                need = max((len + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
+            }
+            int totn;
+            const int before = s_carry[0] + block_scan_excl(need, &totn, s_warp);
+            const int admit = (j < n_cand && before + need <= F) ? 1 : 0;
+            int tota;
+            (void)block_scan_excl(admit, &tota, s_warp);
+            if (admit) {
+                const int row = a.free_rows[j];
+                const int np = min(need, W);
+                for (int t = 0; t < np; ++t)
+                    a.page_table[(size_t)row * W + t] = a.free_ring[(fh + before + t) % a.n_blocks];
+                a.npages[row] = np;
+                a.lengths[row] = len;
+                a.len_shadow[row] = len;
+                a.row_req[row] = id;
+                a.used[n_used + j] = row;
+                a.new_idx[j] = row;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // pages consumed by the admitted prefix of this chunk
+                s_carry[1] += tota;
+                s_carry[0] += totn;
+            }
+            __syncthreads();
+        }
+        const int k_adm = s_carry[1];
+        // pages taken = cumulative need of the first k_adm candidates: recompute exactly
+        __syncthreads();
+        if (tid == 0) {
+            int pages = 0;
+            for (int j = 0; j < k_adm; ++j) {
+                const int id = a.queue[(qh + j) % v->q_cap];
+                pages += max((a.req_cnt[id] + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
+            }
+            s_carry[2] = pages;
+        }
+        __syncthreads();
+        // unoccupied rows that got nothing: length 0 (:109-112)
+        for (int j = k_adm + tid; j < n_free_rows; j += T) {
+            const int row = a.free_rows[j];
+            a.lengths[row] = 0;
+            a.len_shadow[row] = 0;
+        }
+        __syncthreads();
+        // quirk Q1 (:113-118): any unoccupied row => the whole stale host array is copied back
+        if (a.compat && n_free_rows > 0)
+            for (int r = tid; r < B; r += T) a.lengths[r] = a.len_shadow[r];
+        __syncthreads();
+        if (tid == 0) {
+            v->f_head = (fh + s_carry[2]) % a.n_blocks;
+            v->f_count = F - s_carry[2];
+            v->q_head = (qh + k_adm) % v->q_cap;
+            v->q_count = qc - k_adm;
+            v->n_used = n_used + k_adm;
+            v->n_new = k_adm;
+            v->admitted += k_adm;
+            v->iter += 1;
+            // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
+            if (v->n_used + v->q_count == 0) {
+                v->done = 1;
+                *a.done_host = 1;
+                __threadfence_system();
+            } else {
+                v->steps += 1;
+            }
+        }
+    }
+}
+
+__global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats, int max_req) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = gridDim.x * blockDim.x;
+    for (int r = i; r < a.B; r += n) {
+        a.row_req[r] = -1;
+        a.lengths[r] = 0;
+        a.len_shadow[r] = 0;
+        a.npages[r] = 0;
+        a.new_idx[r] = 0;
+        for (int j = 0; j < a.R; ++j) a.dec[(size_t)r * a.R + j] = MLI_EMPTY_ROW_TOKEN_ID;
+    }
+    for (int b = i; b < a.n_blocks; b += n) a.free_ring[b] = pool + (size_t)b * page_floats;
+    for (int q = i; q < max_req; q += n) a.req_cnt[q] = 0;
+    if (i == 0) {
+        SchedVars* v = a.v;
+        v->q_head = 0; v->q_count = 0; v->q_cap = max_req + 1;
+        v->f_head = 0; v->f_count = a.n_blocks;
+        v->n_used = 0; v->n_fin = 0; v->n_new = 0;
+        v->iter = 0; v->done = 0; v->error = 0; v->n_req = 0;
+        v->steps = 0; v->generated = 0; v->preemptions = 0; v->admitted = 0;
+    }
+}
+
+// scatter (offsets, tokens) into the request table and queue every request in id order
+__global__ void engine_submit_kernel(SchedArgs a, const int* __restrict__ offs,
+                                     const int* __restrict__ toks, int n_req) {
+    const int q = blockIdx.x;
+    if (q >= n_req) return;
+    const int o = offs[q], n = offs[q + 1] - o;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) a.req_tok[(size_t)q * a.S + j] = toks[o + j];
+    if (threadIdx.x == 0) {
+        a.req_cnt[q] = n;
+        a.queue[q] = q;
+        if (q == 0) {
+            a.v->q_head = 0;
+            a.v->q_count = n_req;
+            a.v->n_req = n_req;
+        }
+    }
+}
+
+}  // namespace mli
+
+using namespace mli;
+
+struct mli_engine {
+    mli_ctx* ctx = nullptr;
+    mli_engine_cfg cfg{};
+    const float *emb = nullptr, *pos = nullptr, *wk = nullptr, *wq = nullptr, *wv = nullptr;
+    SchedArgs a{};
+    float* pool = nullptr;
+    bool own_pool = false;
+    float *q_out = nullptr, *attn_out = nullptr, *score = nullptr;
+    TileDesc* tiles = nullptr;
+    int* n_tiles = nullptr;
+    int max_tiles = 0;
+    int* done_host = nullptr;  // mapped pinned
+    int* stage_buf = nullptr;  // device staging for host prompts
+    size_t stage_ints = 0;
+    std::vector<void*> allocs;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    int n_req = 0;
+    mli_engine_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ring_ev[4] = {};
+    int* lengths_host = nullptr;  // pinned, profile mode
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(mli_engine* e, T** out, size_t n) {
+    void* p = nullptr;
+    MLI_CUDA(cudaMalloc(&p, sizeof(T) * (n > 0 ? n : 1)));
+    e->allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return 0;
+}
+
+// one engine iteration: scheduler, then n_forward_rounds x the model (inference_model.cpp:52-82)
+int enqueue_step(mli_engine* e, bool profile) {
+    mli_ctx* ctx = e->ctx;
+    const mli_engine_cfg& c = e->cfg;
+    const int B = c.n_batch, S = c.n_sequence, d = c.emb_dim, V = c.n_vocab;
+    int rc;
+    sched_step_kernel<<<1, kSchedThreads, 0, ctx->stream>>>(e->a);
+    MLI_LAUNCH_CHECK();
+    if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0, &e->a.v->n_new, e->tiles,
+                                         e->n_tiles, e->max_tiles)))
+        return rc;
+    if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req, e->a.req_tok,
+                                         e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
+                                         e->a.lengths, S, d)))
+        return rc;
+    const bool tc = (ctx->gemm_mode == 0 && ctx->tc_available);
+    if (tc)
+        rc = launch_prefill_kv_paged_tc(ctx, e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
+                                        e->a.lengths, e->wk, e->wv, S, d);
+    else
+        rc = launch_prefill_kv_paged_simt(ctx, e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
+                                          e->a.lengths, e->wk, e->wv, S, d);
+    if (rc) return rc;
+    for (int round = 0; round < c.n_forward_rounds; ++round) {
+        if (tc)
+            rc = launch_qkv_latest_paged_tc(ctx, e->a.page_table, e->a.lengths, e->wk, e->wq, e->wv,
+                                            e->q_out, B, S, d);
+        else
+            rc = launch_qkv_latest_paged_simt(ctx, e->a.page_table, e->a.lengths, e->wk, e->wq, e->wv,
+                                              e->q_out, B, S, d);
+        if (rc) return rc;
+        if (profile) {
+            ctx->attn_ev_start = e->ev0;
+            ctx->attn_ev_stop = e->ev1;
+        }
+        rc = launch_decode_attention_paged(ctx, e->q_out, e->a.page_table, e->a.lengths, e->attn_out,
+                                           nullptr, B, S, d);
+        ctx->attn_ev_start = ctx->attn_ev_stop = nullptr;
+        if (rc) return rc;
+        if (tc)
+            rc = launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d);
+        else
+            rc = launch_logits_simt(ctx, e->attn_out, e->emb, e->score, B, V, d);
+        if (rc) return rc;
+        if ((rc = launch_paged_decoder(ctx, e->score, e->a.dec, e->a.lengths, e->a.page_table, e->pos,
+                                       e->emb, B, V, S, d, c.n_forward_rounds, round)))
+            return rc;
+    }
+    return 0;
+}
+
+void drop_graph(mli_engine* e) {
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph) cudaGraphDestroy(e->graph);
+    e->graph_exec = nullptr;
+    e->graph = nullptr;
+    e->ctx->ws_frozen = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_table,
+                      const float* pos_table, const float* wk, const float* wq, const float* wv,
+                      mli_engine** out) {
+    MLI_REQUIRE(ctx && cfg && out, "null argument");
+    MLI_REQUIRE(cfg->n_batch > 0 && cfg->n_sequence % kPage == 0 && cfg->emb_dim % 4 == 0 &&
+                    cfg->n_vocab > 0 && cfg->n_blocks > 0 && cfg->max_requests > 0,
+                "bad engine dims");
+    MLI_REQUIRE(cfg->n_forward_rounds >= 1 && cfg->n_forward_rounds <= kPage,
+                "n_forward_rounds must be 1..16");
+    mli_engine* e = new mli_engine();
+    e->ctx = ctx;
+    e->cfg = *cfg;
+    e->emb = emb_table; e->pos = pos_table; e->wk = wk; e->wq = wq; e->wv = wv;
+    const int B = cfg->n_batch, S = cfg->n_sequence, d = cfg->emb_dim, V = cfg->n_vocab;
+    const int W = S / kPage, R = cfg->n_forward_rounds, NR = cfg->max_requests;
+    SchedArgs& a = e->a;
+    a.B = B; a.S = S; a.W = W; a.R = R; a.n_blocks = cfg->n_blocks;
+    a.compat = cfg->compat_stale_lengths;
+    int rc = 0;
+#define A(call) if ((rc = (call))) { mli_engine_destroy(e); return rc; }
+    A(dev_alloc(e, &a.v, 1));
+    A(dev_alloc(e, &a.req_tok, (size_t)NR * S));
+    A(dev_alloc(e, &a.req_cnt, NR));
+    A(dev_alloc(e, &a.queue, NR + 1));
+    A(dev_alloc(e, &a.fin_ids, NR));
+    A(dev_alloc(e, &a.row_req, B));
+    A(dev_alloc(e, &a.lengths, B));
+    A(dev_alloc(e, &a.len_shadow, B));
+    A(dev_alloc(e, &a.used, B));
+    A(dev_alloc(e, &a.npages, B));
+    A(dev_alloc(e, &a.page_table, (size_t)B * W));
+    A(dev_alloc(e, &a.free_ring, cfg->n_blocks));
+    A(dev_alloc(e, &a.dec, (size_t)B * R));
+    A(dev_alloc(e, &a.new_idx, B));
+    A(dev_alloc(e, &a.flag_fin, B));
+    A(dev_alloc(e, &a.flag_free, B));
+    A(dev_alloc(e, &a.need_list, B));
+    A(dev_alloc(e, &a.free_rows, B));
+    A(dev_alloc(e, &a.occ, B));
+    A(dev_alloc(e, &e->q_out, (size_t)B * d));
+    A(dev_alloc(e, &e->attn_out, (size_t)B * d));
+    A(dev_alloc(e, &e->score, (size_t)B * V));
+    e->max_tiles = B * ceil_div(S, kTileM);
+    A(dev_alloc(e, &e->tiles, e->max_tiles));
+    A(dev_alloc(e, &e->n_tiles, 4));
+    const size_t page_floats = (size_t)kPage * 3 * d;
+    if (cfg->page_pool) {
+        e->pool = cfg->page_pool;
+    } else {
+        void* p = nullptr;
+        cudaError_t ce = cudaMalloc(&p, sizeof(float) * page_floats * (size_t)cfg->n_blocks);
+        if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
+        e->pool = reinterpret_cast<float*>(p);
+        e->own_pool = true;
+    }
+    {
+        cudaError_t ce = cudaHostAlloc(reinterpret_cast<void**>(&e->done_host), 64, cudaHostAllocMapped);
+        if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
+        int* dptr = nullptr;
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), e->done_host, 0);
+        a.done_host = dptr;
+        *e->done_host = 0;
+        cudaHostAlloc(reinterpret_cast<void**>(&e->lengths_host), sizeof(int) * (size_t)B,
+                      cudaHostAllocDefault);
+    }
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+    for (auto& ev : e->ring_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+#undef A
+    // zero state so a warm-up step is harmless, then run one un-captured step on the empty engine:
+    // it sizes every workspace the captured graph will later hold pointers to.
+    engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(a, e->pool, page_floats, NR);
+    MLI_LAUNCH_CHECK();
+    if ((rc = enqueue_step(e, false))) { mli_engine_destroy(e); return rc; }
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
+    *out = e;
+    return MLI_OK;
+}
+
+int mli_engine_destroy(mli_engine* e) {
+    if (!e) return MLI_OK;
+    cudaStreamSynchronize(e->ctx->stream);
+    drop_graph(e);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->own_pool && e->pool) cudaFree(e->pool);
+    if (e->stage_buf) cudaFree(e->stage_buf);
+    if (e->done_host) cudaFreeHost(e->done_host);
+    if (e->lengths_host) cudaFreeHost(e->lengths_host);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    for (auto& ev : e->ring_ev)
+        if (ev) cudaEventDestroy(ev);
+    delete e;
+    return MLI_OK;
+}
+
+int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
+                      int is_device) {
+    MLI_REQUIRE(e && prompt_offsets && prompt_tokens, "null argument");
+    MLI_REQUIRE(n_req >= 0 && n_req <= e->cfg.max_requests, "too many requests");
+    mli_ctx* ctx = e->ctx;
+    const size_t page_floats = (size_t)kPage * 3 * e->cfg.emb_dim;
+    const int* d_offs = prompt_offsets;
+    const int* d_toks = prompt_tokens;
+    if (!is_device) {
+        const int total = prompt_offsets[n_req];
+        for (int i = 0; i < n_req; ++i)
+            MLI_REQUIRE(prompt_offsets[i + 1] - prompt_offsets[i] + 1 <= e->cfg.n_sequence &&
+                            prompt_offsets[i + 1] > prompt_offsets[i],
+                        "prompt length must be in [1, n_sequence-1]");
+        const size_t need = (size_t)n_req + 1 + total;
+        if (e->stage_ints < need) {
+            MLI_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (e->stage_buf) cudaFree(e->stage_buf);
+            e->stage_buf = nullptr;
+            MLI_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->stage_buf), sizeof(int) * need));
+            e->stage_ints = need;
+        }
+        MLI_CUDA(cudaMemcpyAsync(e->stage_buf, prompt_offsets, sizeof(int) * ((size_t)n_req + 1),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        MLI_CUDA(cudaMemcpyAsync(e->stage_buf + n_req + 1, prompt_tokens, sizeof(int) * (size_t)total,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        d_offs = e->stage_buf;
+        d_toks = e->stage_buf + n_req + 1;
+    }
+    *e->done_host = 0;
+    engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(e->a, e->pool, page_floats, e->cfg.max_requests);
+    MLI_LAUNCH_CHECK();
+    if (n_req > 0) {
+        engine_submit_kernel<<<n_req, 128, 0, ctx->stream>>>(e->a, d_offs, d_toks, n_req);
+        MLI_LAUNCH_CHECK();
+    }
+    e->n_req = n_req;
+    e->stats = mli_engine_stats{};
+    return MLI_OK;
+}
+
+int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
+    MLI_REQUIRE(e, "null engine");
+    mli_ctx* ctx = e->ctx;
+    int rc;
+    const int B = e->cfg.n_batch, d = e->cfg.emb_dim;
+    float attn_ms = 0.f;
+    double attn_bytes = 0.0;
+    long long attn_launches = 0;
+    MLI_CUDA(cudaEventRecord(e->ring_ev[0], ctx->stream));  // make ring events valid
+    cudaEvent_t t0, t1;
+    MLI_CUDA(cudaEventCreate(&t0));
+    MLI_CUDA(cudaEventCreate(&t1));
+    MLI_CUDA(cudaEventRecord(t0, ctx->stream));
+    long long it = 0;
+    if (profile_attention) {
+        // un-captured, synchronous per step: device time of every fused-attention launch plus the
+        // algorithmic bytes it had to move (from the lengths the launch saw)
+        for (;; ++it) {
+            if (max_steps > 0 && it >= max_steps) break;
+            if (*reinterpret_cast<volatile int*>(e->done_host)) break;
+            // lengths as the attention kernel will see them are only known after the scheduler and
+            // the latest-QKV stage; rounds > 1 are profiled on the first round's lengths + round
+            sched_step_kernel<<<1, kSchedThreads, 0, ctx->stream>>>(e->a);
+            MLI_LAUNCH_CHECK();
+            MLI_CUDA(cudaMemcpyAsync(e->lengths_host, e->a.lengths, sizeof(int) * (size_t)B,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            MLI_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (*reinterpret_cast<volatile int*>(e->done_host)) break;
+            // re-run of the scheduler must not happen: enqueue the rest of the step by hand
+            {
+                const mli_engine_cfg& c = e->cfg;
+                const int S = c.n_sequence, V = c.n_vocab;
+                const bool tc = (ctx->gemm_mode == 0 && ctx->tc_available);
+                if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0,
+                                                     &e->a.v->n_new, e->tiles, e->n_tiles,
+                                                     e->max_tiles)))
+                    return rc;
+                if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req,
+                                                     e->a.req_tok, e->a.page_table, e->tiles,
+                                                     e->n_tiles, e->max_tiles, e->a.lengths, S, d)))
+                    return rc;
+                rc = tc ? launch_prefill_kv_paged_tc(ctx, e->a.page_table, e->tiles, e->n_tiles,
+                                                     e->max_tiles, e->a.lengths, e->wk, e->wv, S, d)
+                        : launch_prefill_kv_paged_simt(ctx, e->a.page_table, e->tiles, e->n_tiles,
+                                                       e->max_tiles, e->a.lengths, e->wk, e->wv, S, d);
+                if (rc) return rc;
+                for (int round = 0; round < c.n_forward_rounds; ++round) {
+                    rc = tc ? launch_qkv_latest_paged_tc(ctx, e->a.page_table, e->a.lengths, e->wk,
+                                                         e->wq, e->wv, e->q_out, B, S, d)
+                            : launch_qkv_latest_paged_simt(ctx, e->a.page_table, e->a.lengths, e->wk,
+                                                           e->wq, e->wv, e->q_out, B, S, d);
+                    if (rc) return rc;
+                    if (round == 0) {
+                        ctx->attn_ev_start = e->ev0;
+                        ctx->attn_ev_stop = e->ev1;
+                    }
+                    rc = launch_decode_attention_paged(ctx, e->q_out, e->a.page_table, e->a.lengths,
+                                                       e->attn_out, nullptr, B, S, d);
+                    ctx->attn_ev_start = ctx->attn_ev_stop = nullptr;
+                    if (rc) return rc;
+                    rc = tc ? launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d)
+                            : launch_logits_simt(ctx, e->attn_out, e->emb, e->score, B, V, d);
+                    if (rc) return rc;
+                    if ((rc = launch_paged_decoder(ctx, e->score, e->a.dec, e->a.lengths,
+                                                   e->a.page_table, e->pos, e->emb, B, V, S, d,
+                                                   c.n_forward_rounds, round)))
+                        return rc;
+                }
+            }
+            MLI_CUDA(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f;
+            MLI_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+            attn_ms += ms;
+            attn_bytes += attention_algorithmic_bytes(e->lengths_host, B, d);
+            ++attn_launches;
+        }
+    } else {
+        if (!e->graph_exec) {
+            MLI_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_step(e, false);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e->graph);
+            if (rc) return rc;
+            if (ce != cudaSuccess) return cuda_fail(ce, __FILE__, __LINE__);
+            MLI_CUDA(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+            ctx->ws_frozen = true;
+        }
+        constexpr int kAhead = 4;
+        for (;; ++it) {
+            if (max_steps > 0 && it >= max_steps) break;
+            if (it >= kAhead) MLI_CUDA(cudaEventSynchronize(e->ring_ev[it % kAhead]));
+            if (*reinterpret_cast<volatile int*>(e->done_host)) break;
+            MLI_CUDA(cudaGraphLaunch(e->graph_exec, ctx->stream));
+            count_launch(4 + 6 * e->cfg.n_forward_rounds);
+            MLI_CUDA(cudaEventRecord(e->ring_ev[it % kAhead], ctx->stream));
+        }
+    }
+    MLI_CUDA(cudaEventRecord(t1, ctx->stream));
+    MLI_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    MLI_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    SchedVars hv;
+    MLI_CUDA(cudaMemcpy(&hv, e->a.v, sizeof(hv), cudaMemcpyDeviceToHost));
+    e->stats.steps = hv.steps;
+    e->stats.generated_tokens = hv.generated;
+    e->stats.preemptions = hv.preemptions;
+    e->stats.admitted = hv.admitted;
+    e->stats.n_finished = hv.n_fin;
+    e->stats.gpu_ms = ms;
+    e->stats.attn_ms = attn_ms;
+    e->stats.attn_bytes = attn_bytes;
+    e->stats.attn_launches = attn_launches;
+    if (hv.error) {
+        set_error("engine: a token arrived for a row that is not processing");
+        return MLI_ERR_STATE;
+    }
+    return MLI_OK;
+}
+
+int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, int* finished_tokens,
+                       int* n_finished) {
+    MLI_REQUIRE(e && finished_ids && finished_offsets && finished_tokens && n_finished,
+                "null argument");
+    mli_ctx* ctx = e->ctx;
+    const int S = e->cfg.n_sequence, NR = e->n_req;
+    MLI_CUDA(cudaStreamSynchronize(ctx->stream));
+    SchedVars hv;
+    MLI_CUDA(cudaMemcpy(&hv, e->a.v, sizeof(hv), cudaMemcpyDeviceToHost));
+    std::vector<int> cnt(NR > 0 ? NR : 1), toks((size_t)(NR > 0 ? NR : 1) * S);
+    MLI_CUDA(cudaMemcpy(finished_ids, e->a.fin_ids, sizeof(int) * (size_t)hv.n_fin,
+                        cudaMemcpyDeviceToHost));
+    MLI_CUDA(cudaMemcpy(cnt.data(), e->a.req_cnt, sizeof(int) * (size_t)NR, cudaMemcpyDeviceToHost));
+    MLI_CUDA(cudaMemcpy(toks.data(), e->a.req_tok, sizeof(int) * (size_t)NR * S,
+                        cudaMemcpyDeviceToHost));
+    int o = 0;
+    for (int i = 0; i < hv.n_fin; ++i) {
+        const int id = finished_ids[i];
+        finished_offsets[i] = o;
+        for (int j = 0; j < cnt[id]; ++j) finished_tokens[o + j] = toks[(size_t)id * S + j];
+        o += cnt[id];
+    }
+    finished_offsets[hv.n_fin] = o;
+    *n_finished = hv.n_fin;
+    return MLI_OK;
+}
+
+int mli_engine_get_stats(mli_engine* e, mli_engine_stats* stats) {
+    MLI_REQUIRE(e && stats, "null argument");
+    *stats = e->stats;
+    return MLI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// kernels.h -- internal launch API shared by the C-ABI glue (capi.cu) and the engine (engine.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace mli {
+
+// M-tile descriptor used by the encoder / prefill kernels: 64 consecutive positions of one row
+struct TileDesc {
+    int row;  // batch row
+    int j0;   // first position of the tile
+};
+constexpr int kTileM = 64;
+
+// ---- tile list for new rows (device-side; lengths never leave the GPU) -----------------------
+// tiles[0..*n_tiles) covers positions [0, L_r) of every new row r in chunks of kTileM.
+// n_new_dev (optional) overrides n_new_host with a device-resident count.
+int launch_build_new_row_tiles(mli_ctx* ctx, const int* new_idx, const int* lengths, int n_new_host,
+                               const int* n_new_dev, TileDesc* tiles, int* n_tiles, int max_tiles);
+
+// ---- encoder (src/kernels/encoder.cu:102-147 / :56-92) ----------------------------------------
+// tokens come from inp[B,S], or (engine) from req_tok[row_req[r]*S + j] when row_req != nullptr
+int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
+                               const int* row_req, const int* req_tok, float* const* page_table,
+                               const TileDesc* tiles, const int* n_tiles, int max_tiles,
+                               const int* lengths, int S, int d);
+int launch_dense_encoder(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
+                         float* inp_embedding, const int* lengths, const int* new_idx, int S, int d,
+                         int n_new);
+
+// ---- exact-order SIMT GEMMs (k-ascending FMA chains == the reference's naive kernels) ----------
+int launch_prefill_kv_paged_simt(mli_ctx* ctx, float* const* page_table, const TileDesc* tiles,
+                                 const int* n_tiles, int max_tiles, const int* lengths,
+                                 const float* wk, const float* wv, int S, int d);
+int launch_qkv_latest_paged_simt(mli_ctx* ctx, float* const* page_table, const int* lengths,
+                                 const float* wk, const float* wq, const float* wv, float* q_output,
+                                 int B, int S, int d);
+int launch_logits_simt(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V,
+                       int d);
+int launch_prefill_kv_dense_simt(mli_ctx* ctx, const float* inp_embedding, const TileDesc* tiles,
+                                 const int* n_tiles, int max_tiles, const int* lengths,
+                                 const float* wk, const float* wv, float* kt_cache, float* v_cache,
+                                 int S, int di, int dn);
+int launch_qkv_latest_dense_simt(mli_ctx* ctx, const float* inp_embedding, const int* lengths,
+                                 const float* wk, const float* wq, const float* wv, float* kt_cache,
+                                 float* v_cache, float* q_output, int B, int S, int di, int dn);
+
+// ---- tcgen05 3xTF32 GEMMs (gemm_tcgen05.cu) ------------------------------------------------------
+bool tcgen05_supported(mli_ctx* ctx);
+int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const TileDesc* tiles,
+                               const int* n_tiles, int max_tiles, const int* lengths,
+                               const float* wk, const float* wv, int S, int d);
+int launch_qkv_latest_paged_tc(mli_ctx* ctx, float* const* page_table, const int* lengths,
+                               const float* wk, const float* wq, const float* wv, float* q_output,
+                               int B, int S, int d);
+int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V,
+                     int d);
+
+// ---- fused decode attention --------------------------------------------------------------------
+int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_table,
+                                  const int* lengths, float* out, float* softmax_out, int B, int S,
+                                  int d);
+int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_cache,
+                                  const float* v_cache, const int* lengths, float* out,
+                                  float* softmax_out, int B, int S, int d);
+double attention_algorithmic_bytes(const int* lengths_host, int B, int d);
+
+// ---- decoder (src/kernels/decoder.cu:25-91, :128-205) -------------------------------------------
+int launch_paged_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
+                         float* const* page_table, const float* pos, const float* emb, int B, int V,
+                         int S, int d, int n_dec, int i_dec);
+int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
+                         float* inp_embedding, const float* pos, const float* emb, int B, int V, int S,
+                         int d);
+
+}  // namespace mli

@@ -1,0 +1,233 @@
+// misc_kernels.cu -- encoder, decoder (argmax / length update / next embedding) and the
+// device-side tile-list builder.  All memory-bound: float4 accesses, one page-pointer load per
+// CTA, grids that are multiples of the SM count where the amount of work is only known on the
+// device.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace mli {
+
+// ---------------------------------------------------------------------------------------------
+// tile list: positions [0, L_r) of every new row, kTileM at a time.  One CTA, block scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void build_new_row_tiles_kernel(const int* __restrict__ new_idx,
+                                           const int* __restrict__ lengths, int n_new_host,
+                                           const int* __restrict__ n_new_dev,
+                                           TileDesc* __restrict__ tiles, int* __restrict__ n_tiles,
+                                           int max_tiles) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int n_new = n_new_dev ? *n_new_dev : n_new_host;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_new; base += blockDim.x) {
+        const int i = base + tid;
+        int r = -1, n = 0;
+        if (i < n_new) {
+            r = new_idx[i];
+            n = (lengths[r] + kTileM - 1) / kTileM;
+        }
+        int v = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = (lane < nwarps) ? warp_tot[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int first = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + v - n;
+        for (int c = 0; c < n; ++c) {
+            if (first + c < max_tiles) {
+                tiles[first + c].row = r;
+                tiles[first + c].j0 = c * kTileM;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry_s = carry + warp_tot[nwarps - 1];
+        __syncthreads();
+    }
+    if (tid == 0) *n_tiles = min(carry_s, max_tiles);
+}
+
+int launch_build_new_row_tiles(mli_ctx* ctx, const int* new_idx, const int* lengths, int n_new_host,
+                               const int* n_new_dev, TileDesc* tiles, int* n_tiles, int max_tiles) {
+    build_new_row_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(new_idx, lengths, n_new_host, n_new_dev,
+                                                            tiles, n_tiles, max_tiles);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// paged encoder (src/kernels/encoder.cu:102-147): page[r][j].inp = E[tok_j] + P[j]
+// persistent CTAs over the tile list; a warp handles one position at a time.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
+                           const int* __restrict__ inp, const int* __restrict__ row_req,
+                           const int* __restrict__ req_tok, float* const* __restrict__ page_table,
+                           const TileDesc* __restrict__ tiles, const int* __restrict__ n_tiles,
+                           const int* __restrict__ lengths, int S, int d) {
+    const int W = S / kPage, d4 = d >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = *n_tiles;
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const TileDesc td = tiles[t];
+        const int L = lengths[td.row];
+        // engine mode: tokens come straight from the device request table (no inp[B,S] copy)
+        const int* toks = row_req ? req_tok + (size_t)row_req[td.row] * S : inp + (size_t)td.row * S;
+        for (int m = warp; m < kTileM; m += 8) {
+            const int j = td.j0 + m;
+            if (j >= L) break;
+            const int tok = toks[j];
+            const float4* e = reinterpret_cast<const float4*>(emb + (size_t)tok * d);
+            const float4* p = reinterpret_cast<const float4*>(pos + (size_t)j * d);
+            float4* x = reinterpret_cast<float4*>(
+                page_row_ptr(page_table[(size_t)td.row * W + j / kPage], j, d, 0));
+            for (int c = lane; c < d4; c += 32) {
+                const float4 a = __ldg(e + c), b = __ldg(p + c);
+                x[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            }
+        }
+    }
+}
+
+int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
+                               const int* row_req, const int* req_tok, float* const* page_table,
+                               const TileDesc* tiles, const int* n_tiles, int max_tiles,
+                               const int* lengths, int S, int d) {
+    int grid = ctx->num_sms * 4;
+    if (grid > max_tiles) grid = max_tiles;
+    if (grid < 1) grid = 1;
+    paged_encoder_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(emb, pos, inp, row_req, req_tok,
+                                                              page_table, tiles, n_tiles, lengths, S,
+                                                              d);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+// dense encoder (src/kernels/encoder.cu:56-92); element-wise so any emb_dim works
+__global__ void dense_encoder_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
+                                     const int* __restrict__ inp, float* __restrict__ out,
+                                     const int* __restrict__ lengths,
+                                     const int* __restrict__ new_idx, int S, int d) {
+    const int r = new_idx[blockIdx.y];
+    const int L = lengths[r];
+    for (int j = blockIdx.x; j < L; j += gridDim.x) {
+        const int tok = inp[(size_t)r * S + j];
+        const float* e = emb + (size_t)tok * d;
+        const float* p = pos + (size_t)j * d;
+        float* x = out + ((size_t)r * S + j) * d;
+        for (int c = threadIdx.x; c < d; c += blockDim.x) x[c] = e[c] + p[c];
+    }
+}
+
+int launch_dense_encoder(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
+                         float* inp_embedding, const int* lengths, const int* new_idx, int S, int d,
+                         int n_new) {
+    if (n_new <= 0) return 0;
+    dim3 grid(S < 64 ? S : 64, n_new);
+    dense_encoder_kernel<<<grid, 128, 0, ctx->stream>>>(emb, pos, inp, inp_embedding, lengths,
+                                                        new_idx, S, d);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder (src/kernels/decoder.cu:128-205 paged, :25-91 dense).  One 256-thread CTA per row.
+// The argmax reproduces the reference's tie-break exactly: thread t scans
+// indices t, t+256, ... keeping the first strict maximum, then a shared-memory tree in which the
+// lower thread wins ties.  lengths = L+1, or 0 when token == EOF or L+1 >= S; otherwise the next
+// input embedding E[token] + P[L] is written for position L.
+// ---------------------------------------------------------------------------------------------
+template <bool PAGED>
+__global__ void __launch_bounds__(256)
+decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result,
+               int* __restrict__ lengths, float* const* __restrict__ page_table,
+               float* __restrict__ inp_embedding, const float* __restrict__ pos,
+               const float* __restrict__ emb, int V, int S, int d, int n_dec, int i_dec) {
+    const int r = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int L = lengths[r];
+    if (L == 0) {
+        if (tid == 0) decoder_result[(size_t)r * n_dec + i_dec] = MLI_EMPTY_ROW_TOKEN_ID;
+        return;
+    }
+    __shared__ float mv[256];
+    __shared__ int mi[256];
+    const float* s = score + (size_t)r * V;
+    float lm = -FLT_MAX;
+    int li = -1;
+    for (int i = tid; i < V; i += 256) {
+        const float v = s[i];
+        if (v > lm) { lm = v; li = i; }
+    }
+    mv[tid] = lm;
+    mi[tid] = li;
+    __syncthreads();
+    for (int gap = 128; gap > 0; gap >>= 1) {
+        if (tid < gap) {
+            if (mv[tid + gap] > mv[tid]) { mv[tid] = mv[tid + gap]; mi[tid] = mi[tid + gap]; }
+        }
+        __syncthreads();
+    }
+    const int tok = mi[0];
+    const bool stop = (tok == MLI_EOF_TOKEN_ID) || (L + 1 >= S);
+    if (tid == 0) {
+        decoder_result[(size_t)r * n_dec + i_dec] = tok;
+        lengths[r] = stop ? 0 : L + 1;
+    }
+    if (stop) return;
+    float* x;
+    if (PAGED) {
+        x = page_row_ptr(page_table[(size_t)r * (S / kPage) + L / kPage], L, d, 0);
+    } else {
+        x = inp_embedding + ((size_t)r * S + L) * d;
+    }
+    const float* e = emb + (size_t)tok * d;
+    const float* p = pos + (size_t)L * d;
+    if ((d & 3) == 0) {
+        const int d4 = d >> 2;
+        for (int c = tid; c < d4; c += 256) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(e) + c);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p) + c);
+            reinterpret_cast<float4*>(x)[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+    } else {
+        for (int c = tid; c < d; c += 256) x[c] = e[c] + p[c];
+    }
+}
+
+int launch_paged_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
+                         float* const* page_table, const float* pos, const float* emb, int B, int V,
+                         int S, int d, int n_dec, int i_dec) {
+    decoder_kernel<true><<<B, 256, 0, ctx->stream>>>(score, decoder_result, lengths, page_table,
+                                                     nullptr, pos, emb, V, S, d, n_dec, i_dec);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
+                         float* inp_embedding, const float* pos, const float* emb, int B, int V, int S,
+                         int d) {
+    decoder_kernel<false><<<B, 256, 0, ctx->stream>>>(score, decoder_result, lengths, nullptr,
+                                                      inp_embedding, pos, emb, V, S, d, 1, 0);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mli
