@@ -435,7 +435,26 @@ struct mli_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ring_ev[4] = {};
     int* lengths_host = nullptr;  // pinned, profile mode
+    // the engine runs on its own non-blocking stream: the caller's stream may be the legacy
+    // default stream, which cannot be captured into a graph
+    cudaStream_t stream = nullptr;
+    cudaEvent_t join_ev = nullptr;
 };
+
+namespace {
+// while alive, every launch helper (they take the stream from the context) targets the engine's
+// stream, ordered after whatever the caller already enqueued on the context's stream
+struct StreamScope {
+    mli_ctx* ctx;
+    cudaStream_t saved;
+    StreamScope(mli_engine* e) : ctx(e->ctx), saved(e->ctx->stream) {
+        cudaEventRecord(e->join_ev, saved);
+        cudaStreamWaitEvent(e->stream, e->join_ev, 0);
+        ctx->stream = e->stream;
+    }
+    ~StreamScope() { ctx->stream = saved; }
+};
+}  // namespace
 
 namespace {
 
@@ -579,7 +598,13 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
     for (auto& ev : e->ring_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming);
+    {
+        cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
+    }
 #undef A
+    StreamScope scope(e);
     // zero state so a warm-up step is harmless, then run one un-captured step on the empty engine:
     // it sizes every workspace the captured graph will later hold pointers to.
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(a, e->pool, page_floats, NR);
@@ -594,7 +619,10 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
 int mli_engine_destroy(mli_engine* e) {
     if (!e) return MLI_OK;
     cudaStreamSynchronize(e->ctx->stream);
+    if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graph(e);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->join_ev) cudaEventDestroy(e->join_ev);
     for (void* p : e->allocs) cudaFree(p);
     if (e->own_pool && e->pool) cudaFree(e->pool);
     if (e->stage_buf) cudaFree(e->stage_buf);
@@ -613,6 +641,7 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
     MLI_REQUIRE(e && prompt_offsets && prompt_tokens, "null argument");
     MLI_REQUIRE(n_req >= 0 && n_req <= e->cfg.max_requests, "too many requests");
     mli_ctx* ctx = e->ctx;
+    StreamScope scope(e);
     const size_t page_floats = (size_t)kPage * 3 * e->cfg.emb_dim;
     const int* d_offs = prompt_offsets;
     const int* d_toks = prompt_tokens;
@@ -652,6 +681,7 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
 int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     MLI_REQUIRE(e, "null engine");
     mli_ctx* ctx = e->ctx;
+    StreamScope scope(e);
     int rc;
     const int B = e->cfg.n_batch, d = e->cfg.emb_dim;
     float attn_ms = 0.f;
@@ -730,8 +760,12 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             MLI_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             rc = enqueue_step(e, false);
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e->graph);
-            if (rc) return rc;
-            if (ce != cudaSuccess) return cuda_fail(ce, __FILE__, __LINE__);
+            if (rc || ce != cudaSuccess) {
+                if (e->graph) cudaGraphDestroy(e->graph);
+                e->graph = nullptr;
+                cudaGetLastError();
+                return rc ? rc : cuda_fail(ce, __FILE__, __LINE__);
+            }
             MLI_CUDA(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
             ctx->ws_frozen = true;
         }
@@ -775,6 +809,7 @@ int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, 
                 "null argument");
     mli_ctx* ctx = e->ctx;
     const int S = e->cfg.n_sequence, NR = e->n_req;
+    MLI_CUDA(cudaStreamSynchronize(e->stream));
     MLI_CUDA(cudaStreamSynchronize(ctx->stream));
     SchedVars hv;
     MLI_CUDA(cudaMemcpy(&hv, e->a.v, sizeof(hv), cudaMemcpyDeviceToHost));

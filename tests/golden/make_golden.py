@@ -33,7 +33,7 @@ def stages(out, name, B, S, d, V, dist, case_seed, w_seed, eof_ratio=1.3):
     n_new = len(cand) // 2 + 1
     new_idx = np.zeros(B, np.int32)
     new_idx[:n_new] = cand[:n_new]
-    inp = rng.integers(0, 1023, size=(B, S)).astype(np.int32)
+    inp = rng.integers(0, min(V, 1023), size=(B, S)).astype(np.int32)
     dw = {k: dev(v) for k, v in w.items()}
     pool, tab = case.device(torch)
     dL, dnew, dinp = dev(L), dev(new_idx), dev(inp)

@@ -30,7 +30,7 @@ def test_oracle_equals_reference_cuda(torch_cuda, ref, B, S, d, V, dist):
     cand = np.flatnonzero(L > 0)
     n_new = len(cand) // 2 + 1
     new_idx[:n_new] = cand[:n_new]
-    inp = rng.integers(0, 1023, size=(B, S)).astype(np.int32)
+    inp = rng.integers(0, min(V, 1023), size=(B, S)).astype(np.int32)
     # ---- oracle (host) ----
     hpool, htab = case.host()
     hq = np.zeros((B, d), np.float32)
