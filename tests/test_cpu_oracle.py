@@ -178,7 +178,8 @@ def test_admission_rule_q6():
 @pytest.mark.skipif(not list(GOLDEN.glob("ref_cuda_*.npz")), reason="no golden vectors committed yet")
 @pytest.mark.parametrize("path", sorted(GOLDEN.glob("ref_cuda_*.npz")), ids=lambda p: p.stem)
 def test_oracle_against_reference_cuda_golden(path):
-    g = np.load(path, allow_pickle=False)
+    with np.load(path, allow_pickle=False) as z:
+        g = {k: np.ascontiguousarray(z[k]) for k in z.files}   # keep arrays alive: H.p() takes raw pointers
     kind = str(g["kind"])
     if kind == "stages":
         B, S, d, V = (int(g[k]) for k in ("B", "S", "d", "V"))
