@@ -179,7 +179,7 @@ def test_admission_rule_q6():
 @pytest.mark.parametrize("path", sorted(GOLDEN.glob("ref_cuda_*.npz")), ids=lambda p: p.stem)
 def test_oracle_against_reference_cuda_golden(path):
     with np.load(path, allow_pickle=False) as z:
-        g = {k: np.ascontiguousarray(z[k]) for k in z.files}   # keep arrays alive: H.p() takes raw pointers
+        g = {k: (z[k].item() if z[k].ndim == 0 else np.ascontiguousarray(z[k])) for k in z.files}  # keep arrays alive: H.p() takes raw pointers
     kind = str(g["kind"])
     if kind == "stages":
         B, S, d, V = (int(g[k]) for k in ("B", "S", "d", "V"))
