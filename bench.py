@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of the paged-attention decode path (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- paged attention, page_size 16, n_batch 256,
+emb_dim 1024, n_sequence 128, vocab 1024, pool 1024 pages, 512 requests with prompt lengths
+U[1,64], n_forward_rounds 1 (the reference's tests/paged_for_profile.cpp workload at the
+BASELINE-named shape; SURVEY 8d "C2a").  Synthetic, fixed seeds, zero-mean weights (dist "Z": the
+reference's U(0,1] fixtures make softmax one-hot and every row emit the same token; SURVEY
+finding 9), corrected lengths (the reference's quirk Q1 is replayed only in the parity tests).
+
+A "step" = one whole engine job: all requests admitted, prefilled, decoded to EOS / n_sequence and
+retired by the on-device scheduler.  `value` = generated tokens / device time with the prompts
+already resident in HBM; `e2e` = the same job through the host-buffer C ABI (prompts H2D from
+pinned memory, finished token lists D2H) by wall clock.  With N > 1 (torchrun) every rank runs the
+same-sized job on its own requests (weak scaling, request sharding; no collective on the data
+path) and the final tokens are all-gathered over NCCL inside the timed region.
+
+`--impl reference` times the reference's own HOST implementation of the path (oracle/_ref:
+tests/test_utils.cpp host loops driven by the reference's scheduler; single-threaded as written) on
+a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests"))
+
+WORKLOAD = dict(name="BASELINE.json configs[1]: paged attention, n_batch=256, emb_dim=1024, "
+                     "n_sequence=128, page_size=16, pool=1024 pages, 512 requests, prompts U[1,64]",
+                B=256, S=128, d=1024, V=1024, n_blocks=1024, n_req=512, lo=1, hi=64, R=1)
+METRIC = "decode tokens/sec (paged attention, continuous batching)"
+UNIT = "tokens/s"
+
+
+def peaks():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9])
+                          if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """the reference's own CPU implementation of the path (oracle/_ref), bounded sample"""
+    if rank != 0:
+        return
+    import harness as H
+    wl = WORKLOAD
+    sample_rows, sample_iters = 16, 8
+    w = H.make_weights(1001, wl["d"], wl["V"], wl["S"], "Z")
+    offs, toks = H.make_prompts(2002, wl["n_req"], wl["lo"], wl["hi"])
+    offs_s = offs[:sample_rows + 1].copy()
+    toks_s = toks[:offs_s[-1]].copy()
+    sample = (f"first {sample_rows} of {wl['n_req']} requests on {sample_rows} rows, prefill + "
+              f"{sample_iters} engine iterations per step, same d/S/V/prompt distribution")
+    times, gens = [], []
+    if H.ref_available():
+        import torch  # the reference's host tensors are cudaHostAlloc'd: needs a CUDA context
+        torch.cuda.init()
+        ref = H.load_ref()
+        kind, cores = "reference", 1
+        for i in range(args.warmup + args.steps):
+            gen, steps, sec = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
+            H.check_ref(ref.ref_run_host_engine(sample_rows, wl["S"], wl["d"], wl["V"], H.p(w["emb"]),
+                                                H.p(w["pos"]), H.p(w["wk"]), H.p(w["wq"]), H.p(w["wv"]),
+                                                sample_rows, H.p(offs_s), H.p(toks_s), sample_iters,
+                                                C.byref(gen), C.byref(steps), C.byref(sec), None, None,
+                                                None, None))
+            if i >= args.warmup:
+                times.append(sec.value)
+                gens.append(gen.value)
+    else:
+        kind, cores = "port", os.cpu_count() or 1
+        cfg = dict(B=sample_rows, S=wl["S"], d=wl["d"], V=wl["V"], n_blocks=sample_rows * 8, R=1)
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            rc, _, _, st = H.run_oracle_engine("paged", cfg, w, offs_s, toks_s, fix=1,
+                                               max_steps=sample_iters, threads=cores)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+                gens.append(st.generated_tokens)
+    total_t, total_g = float(sum(times)), float(sum(gens))
+    value = total_g / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD["name"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline_leg():
+    """oracle port (OpenMP over rows) on all host cores, bounded sample of the same workload"""
+    import harness as H
+    wl = WORKLOAD
+    cores = os.cpu_count() or 1
+    iters = 24
+    w = H.make_weights(1001, wl["d"], wl["V"], wl["S"], "Z")
+    offs, toks = H.make_prompts(2002, wl["n_req"], wl["lo"], wl["hi"])
+    cfg = dict(B=wl["B"], S=wl["S"], d=wl["d"], V=wl["V"], n_blocks=wl["n_blocks"], R=1)
+    t0 = time.perf_counter()
+    rc, _, _, st = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1, max_steps=iters, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": st.generated_tokens / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"full workload shape, first {iters} engine iterations incl. the initial prefill of "
+                      f"{wl['B']} rows ({st.generated_tokens} tokens in {dt:.1f} s), OpenMP over rows"}
+
+
+def reference_cuda_leg(w, offs, toks):
+    """the reference's CUDA engines (rebuilt for sm_100) on the same tensors, their own metric:
+    generated tokens / wall time including host scheduling (src/throughput_counter.cpp)"""
+    import harness as H
+    if not H.ref_available():
+        return None
+    ref = H.load_ref()
+    wl = WORKLOAD
+    n_req, S = wl["n_req"], wl["S"]
+    out = {}
+    for name, variant in (("warp_tiling_cublas", 1), ("naive", 0)):
+        ids = np.zeros(n_req, np.int32)
+        fo = np.zeros(n_req + 1, np.int32)
+        ft = np.zeros(n_req * S, np.int32)
+        nf, sec = C.c_int(0), C.c_double(0)
+        best = None
+        for _ in range(2):
+            H.check_ref(ref.ref_run_paged_engine(variant, wl["B"], S, wl["d"], wl["V"], wl["n_blocks"], 1,
+                                                 H.p(w["emb"]), H.p(w["pos"]), H.p(w["wk"]), H.p(w["wq"]),
+                                                 H.p(w["wv"]), n_req, H.p(offs), H.p(toks), H.p(ids),
+                                                 H.p(fo), H.p(ft), C.byref(nf), C.byref(sec)))
+            gen = int(fo[nf.value]) - int(offs[-1])
+            tps = gen / sec.value
+            best = tps if best is None else max(best, tps)
+        out[name + "_tok_s"] = best
+        out[name + "_tokens"] = gen
+    out["note"] = ("reference engines replay quirk Q1 (stale lengths): their rows attend over at most the "
+                   "prompt length; same prompts/weights as our arm")
+    return out
+
+
+def long_context_leg(ctx, torch, hbm_peak):
+    """fused decode attention alone at a BASELINE configs[2]-like shape (HBM-bound regime):
+    B=1024, d=2048, context lengths U[64,2048]; inputs (26 GB of KV pages) far larger than L2"""
+    import harness as H
+    import min_llm_inference_b200 as mli
+    B, S, d = 1024, 2048, 2048
+    rng = np.random.default_rng(7)
+    L = rng.integers(64, S, size=B).astype(np.int32)
+    W = S // 16
+    need = (L + 15) // 16
+    n_pages = int(need.sum())
+    page_floats = 16 * 3 * d
+    try:
+        pool = torch.empty((n_pages, page_floats), device="cuda", dtype=torch.float32)
+    except Exception as e:  # not enough memory on a shared box
+        return {"skipped": str(e)[:80]}
+    for i in range(0, n_pages, 4096):
+        pool[i:i + 4096].uniform_(-1.0, 1.0)
+    perm = rng.permutation(n_pages)
+    tab = np.zeros((B, W), np.uint64)
+    k = 0
+    for r in range(B):
+        ids = perm[k:k + need[r]]
+        tab[r, :need[r]] = np.uint64(pool.data_ptr()) + ids.astype(np.uint64) * np.uint64(page_floats * 4)
+        k += need[r]
+    dtab = torch.from_numpy(tab.view(np.int64)).cuda()
+    dL = torch.from_numpy(L).cuda()
+    q = (torch.rand((B, d), device="cuda") - 0.5) * 0.1
+    out = torch.empty((B, d), device="cuda")
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        ctx.call("mli_decode_attention_paged", q, dtab, dL, out, None, B, S, d)
+    torch.cuda.synchronize()
+    n = 10
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(n):
+        ctx.call("mli_decode_attention_paged", q, dtab, dL, out, None, B, S, d)
+    t1.record(stream)
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / n
+    nbytes = float(np.sum(8.0 * d * L + 8.0 * d + 8.0 * need + 4.0))
+    gbs = nbytes / ms / 1e6
+    del pool
+    return {"workload": "fused decode attention alone, B=1024, d=2048, L~U[64,2048] (BASELINE configs[2] shape)",
+            "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            "ms_per_launch": ms, "algorithmic_bytes": nbytes,
+            "note": "3 launches per call (item list, attention, split combine) timed together"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference CUDA / long-context legs")
+    ap.add_argument("--gemm-mode", type=int, default=-1, help="override MLI_OPT_GEMM_MODE (0 tcgen05, 1 SIMT exact)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import harness as H
+    import min_llm_inference_b200 as mli
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = WORKLOAD
+    B, S, d, V = wl["B"], wl["S"], wl["d"], wl["V"]
+    hbm_peak, peak_src = peaks()
+
+    ctx = mli.Context(local_rank, torch.cuda.current_stream().cuda_stream)
+    if args.gemm_mode >= 0:
+        ctx.set_option(mli.OPT_GEMM_MODE, args.gemm_mode)
+    gemm_mode = ctx.get_option(mli.OPT_GEMM_MODE)
+
+    # same weights on every rank (replicated; each rank regenerates them from the seed), its own requests
+    w = H.make_weights(1001, d, V, S, "Z")
+    offs, toks = H.make_prompts(2002 + rank, wl["n_req"], wl["lo"], wl["hi"])
+    dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None)
+    eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+    d_offs, d_toks = torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda()
+    p_offs = torch.from_numpy(offs).pin_memory()
+    p_toks = torch.from_numpy(toks).pin_memory()
+    tok_buf = torch.zeros((wl["n_req"], S), dtype=torch.int32, device="cuda")
+    cnt_buf = torch.zeros((wl["n_req"],), dtype=torch.int32, device="cuda")
+    gather_tok = torch.zeros((world, wl["n_req"], S), dtype=torch.int32, device="cuda") if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def job_device():
+        """one step, prompts resident in HBM; returns (device ms, tokens generated)"""
+        eng.submit(d_offs, d_toks, is_device=True)
+        eng.run()
+        st = eng.stats()
+        ms = st.gpu_ms
+        if world > 1:   # the only collective of the path: final token gather
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.copy_tokens(tok_buf, cnt_buf)
+            dist.all_gather_into_tensor(gather_tok.view(-1), tok_buf.view(-1))
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms, st.generated_tokens
+
+    def job_e2e():
+        """one step through the host-buffer C ABI: prompts H2D, finished token lists D2H"""
+        eng.submit(p_offs.numpy(), p_toks.numpy(), is_device=False)
+        eng.run()
+        res, order = eng.results()
+        return eng.stats().generated_tokens, len(order)
+
+    for _ in range(args.warmup):
+        job_device()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms, gen_total = 0.0, 0
+    for _ in range(args.steps):
+        ms, gen = job_device()
+        dev_ms += ms
+        gen_total += gen
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    st = eng.stats()
+
+    # e2e (wall clock, host buffers)
+    job_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_gen = 0
+    for _ in range(args.steps):
+        g, nfin = job_e2e()
+        e2e_gen += g
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = 4 * (len(offs) + len(toks))
+    d2h = 4 * (nfin + wl["n_req"] + wl["n_req"] * S) + 128
+
+    # roofline pass: every fused-attention launch of one job bracketed by CUDA events
+    eng.submit(d_offs, d_toks, is_device=True)
+    eng.run(profile_attention=True)
+    ps = eng.stats()
+    attn_gbs = ps.attn_bytes / max(ps.attn_ms, 1e-9) / 1e6
+
+    # reduce over ranks: max time, sum tokens
+    stats_t = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    toks_t = torch.tensor([float(gen_total), float(e2e_gen), float(launches)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(toks_t, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, e2e_ms_max = (float(x) for x in stats_t.tolist())
+    gen_all, e2e_gen_all, launches_all = (float(x) for x in toks_t.tolist())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": gen_all / (dev_ms_max / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "n_batch": B, "emb_dim": d, "n_sequence": S, "n_vocab": V,
+                       "kv_pages": wl["n_blocks"], "requests_per_gpu": wl["n_req"], "n_forward_rounds": 1,
+                       "distribution": "Z (zero-mean), fixed seeds", "lengths": "corrected (no Q1 replay)",
+                       "gemm_mode": "tcgen05 3xTF32" if gemm_mode == 0 else "SIMT fp32 exact-order",
+                       "l2": "inputs larger than L2 (KV pool 201 MB + tables > 126 MB); no flush",
+                       "parallelism": f"request-sharded dp{world}",
+                       "step": "one whole engine job (512 requests per GPU to completion)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_gen_all / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "timed_by": "wall clock, host buffers through the C ABI"},
+            "gpu_launches": int(launches_all),
+            "tokens_per_step": gen_all / args.steps, "engine_iterations_per_step": st.steps,
+            "preemptions_per_step": st.preemptions, "wall_ms_per_step": wall_ms_max / args.steps,
+            "roofline": {"kernel": "decode_attention_kernel (fused qkt+softmax+softmax_v, split-KV)",
+                         "bound": "hbm", "achieved": attn_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": attn_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "launches": ps.attn_launches, "avg_launch_us": 1e3 * ps.attn_ms / max(1, ps.attn_launches),
+                         "algorithmic_bytes_per_launch": ps.attn_bytes / max(1, ps.attn_launches),
+                         "note": "ATTN_BYTES (SURVEY 8d) / CUDA-event time of every attention launch of one job"},
+        }
+        if world == 1 and not args.no_extras:
+            try:
+                # its own context: the engine's captured graph pins the first context's workspaces
+                ctx2 = mli.Context(local_rank, torch.cuda.current_stream().cuda_stream)
+                line["roofline_long_context"] = long_context_leg(ctx2, torch, hbm_peak)
+                ctx2.close()
+            except Exception as e:  # never lose the headline line to an extra
+                line["roofline_long_context"] = {"error": str(e)[:200]}
+            try:
+                line["reference_cuda"] = reference_cuda_leg(w, offs, toks)
+            except Exception as e:
+                line["reference_cuda"] = {"error": str(e)[:200]}
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg()
+            except Exception as e:
+                line["cpu_baseline"] = {"error": str(e)[:200]}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -175,7 +175,9 @@ typedef struct {
     long long preemptions;
     long long admitted;
     int n_finished;
-    float gpu_ms;               /* device time of the last mli_engine_run (CUDA events) */
+    float gpu_ms;               /* device time (CUDA events on the engine's stream) from the start
+                                   of the mli_engine_submit that fed it to the end of the last
+                                   mli_engine_run */
     float attn_ms;              /* device time spent in the fused decode-attention kernels, only
                                    when profiling was requested (else 0) */
     double attn_bytes;          /* algorithmic bytes of those launches (SURVEY 8d ATTN_BYTES) */
@@ -199,6 +201,10 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention);
  * tokens[n_req * n_sequence] (prompt + generated) */
 int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, int* finished_tokens,
                        int* n_finished);
+/* device-to-device copy of the request table (tokens[n_req][n_sequence], counts[n_req]) into
+ * caller buffers on the context's stream -- what the multi-GPU token gather (NCCL all-gather,
+ * the only collective of the path) sends */
+int mli_engine_copy_tokens(mli_engine* e, int* tokens_dev, int* counts_dev);
 int mli_engine_get_stats(mli_engine* e, mli_engine_stats* stats);
 
 #ifdef __cplusplus

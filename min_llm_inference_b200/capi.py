@@ -72,6 +72,7 @@ SIGNATURES = {
     "mli_engine_submit": (_I, [_P, _I, _P, _P, _I]),
     "mli_engine_run": (_I, [_P, _LL, _I]),
     "mli_engine_results": (_I, [_P, _P, _P, _P, C.POINTER(_I)]),
+    "mli_engine_copy_tokens": (_I, [_P, _P, _P]),
     "mli_engine_get_stats": (_I, [_P, C.POINTER(EngineStats)]),
 }
 
@@ -215,6 +216,9 @@ class Engine:
                                                     toks.ctypes.data, C.byref(nf)))
         k = nf.value
         return {int(ids[i]): toks[offs[i]:offs[i + 1]].copy() for i in range(k)}, ids[:k].copy()
+
+    def copy_tokens(self, tokens_dev, counts_dev):
+        self.ctx._check(self.lib.mli_engine_copy_tokens(self.h, _ptr(tokens_dev), _ptr(counts_dev)))
 
     def stats(self) -> EngineStats:
         st = EngineStats()

@@ -433,6 +433,8 @@ struct mli_engine {
     int n_req = 0;
     mli_engine_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_submit = nullptr, ev_end = nullptr;  // job timing: start of submit .. end of run
+    bool submit_timed = false;
     cudaEvent_t ring_ev[4] = {};
     int* lengths_host = nullptr;  // pinned, profile mode
     // the engine runs on its own non-blocking stream: the caller's stream may be the legacy
@@ -597,6 +599,8 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     }
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
+    cudaEventCreate(&e->ev_submit);
+    cudaEventCreate(&e->ev_end);
     for (auto& ev : e->ring_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming);
     {
@@ -630,6 +634,8 @@ int mli_engine_destroy(mli_engine* e) {
     if (e->lengths_host) cudaFreeHost(e->lengths_host);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_submit) cudaEventDestroy(e->ev_submit);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
     for (auto& ev : e->ring_ev)
         if (ev) cudaEventDestroy(ev);
     delete e;
@@ -645,6 +651,8 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
     const size_t page_floats = (size_t)kPage * 3 * e->cfg.emb_dim;
     const int* d_offs = prompt_offsets;
     const int* d_toks = prompt_tokens;
+    MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
+    e->submit_timed = true;
     if (!is_device) {
         const int total = prompt_offsets[n_req];
         for (int i = 0; i < n_req; ++i)
@@ -688,10 +696,9 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     double attn_bytes = 0.0;
     long long attn_launches = 0;
     MLI_CUDA(cudaEventRecord(e->ring_ev[0], ctx->stream));  // make ring events valid
-    cudaEvent_t t0, t1;
-    MLI_CUDA(cudaEventCreate(&t0));
-    MLI_CUDA(cudaEventCreate(&t1));
-    MLI_CUDA(cudaEventRecord(t0, ctx->stream));
+    // device time of the job: from the start of the submit that fed this run (else from here)
+    if (!e->submit_timed) MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
+    e->submit_timed = false;
     long long it = 0;
     if (profile_attention) {
         // un-captured, synchronous per step: device time of every fused-attention launch plus the
@@ -779,12 +786,10 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             MLI_CUDA(cudaEventRecord(e->ring_ev[it % kAhead], ctx->stream));
         }
     }
-    MLI_CUDA(cudaEventRecord(t1, ctx->stream));
+    MLI_CUDA(cudaEventRecord(e->ev_end, ctx->stream));
     MLI_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    MLI_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
+    MLI_CUDA(cudaEventElapsedTime(&ms, e->ev_submit, e->ev_end));
     SchedVars hv;
     MLI_CUDA(cudaMemcpy(&hv, e->a.v, sizeof(hv), cudaMemcpyDeviceToHost));
     e->stats.steps = hv.steps;
@@ -828,6 +833,18 @@ int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, 
     }
     finished_offsets[hv.n_fin] = o;
     *n_finished = hv.n_fin;
+    return MLI_OK;
+}
+
+int mli_engine_copy_tokens(mli_engine* e, int* tokens_dev, int* counts_dev) {
+    MLI_REQUIRE(e && tokens_dev && counts_dev, "null argument");
+    mli_ctx* ctx = e->ctx;
+    MLI_CUDA(cudaStreamSynchronize(e->stream));
+    MLI_CUDA(cudaMemcpyAsync(tokens_dev, e->a.req_tok,
+                             sizeof(int) * (size_t)e->n_req * e->cfg.n_sequence,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    MLI_CUDA(cudaMemcpyAsync(counts_dev, e->a.req_cnt, sizeof(int) * (size_t)e->n_req,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
     return MLI_OK;
 }
 
