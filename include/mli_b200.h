@@ -60,6 +60,13 @@ int mli_ctx_set_stream(mli_ctx* ctx, void* cuda_stream);
 int mli_ctx_set_option(mli_ctx* ctx, int option, int value);
 int mli_ctx_get_option(mli_ctx* ctx, int option, int* value);
 int mli_ctx_synchronize(mli_ctx* ctx);
+/* tcgen05 mode keeps tf32-split, K-major copies of the weight operands.  Registered pointers are
+ * split once and trusted to stay unchanged until unregistered (what a layer that owns its weights
+ * does: the reference's *Layer classes take them by &&, include/layers.h:54-100); unregistered
+ * pointers are re-split on every call.  Any argument may be NULL. */
+int mli_ctx_register_weights(mli_ctx* ctx, const float* wk, const float* wq, const float* wv,
+                             const float* emb_table, int emb_dim, int n_vocab);
+int mli_ctx_unregister_weights(mli_ctx* ctx);
 const char* mli_last_error(void);
 const char* mli_version(void);
 /* number of kernels this library has launched in this process (bench.py reports it) */

@@ -53,6 +53,8 @@ SIGNATURES = {
     "mli_ctx_set_option": (_I, [_P, _I, _I]),
     "mli_ctx_get_option": (_I, [_P, _I, C.POINTER(_I)]),
     "mli_ctx_synchronize": (_I, [_P]),
+    "mli_ctx_register_weights": (_I, [_P, _P, _P, _P, _P, _I, _I]),
+    "mli_ctx_unregister_weights": (_I, [_P]),
     "mli_last_error": (C.c_char_p, []),
     "mli_version": (C.c_char_p, []),
     "mli_kernel_launch_count": (_LL, []),
@@ -164,6 +166,13 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.mli_ctx_synchronize(self.h))
+
+    def register_weights(self, wk, wq, wv, emb, emb_dim, n_vocab):
+        self._check(self.lib.mli_ctx_register_weights(self.h, _ptr(wk), _ptr(wq), _ptr(wv), _ptr(emb),
+                                                      emb_dim, n_vocab))
+
+    def unregister_weights(self):
+        self._check(self.lib.mli_ctx_unregister_weights(self.h))
 
     def set_stream(self, stream):
         self._check(self.lib.mli_ctx_set_stream(self.h, stream))

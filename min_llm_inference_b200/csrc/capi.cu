@@ -122,6 +122,7 @@ int mli_ctx_create(mli_ctx** out, int device, void* cuda_stream) {
 int mli_ctx_destroy(mli_ctx* ctx) {
     if (!ctx) return MLI_OK;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->tc_available) tc_unregister_all(ctx);
     for (int i = 0; i < WS_NUM_SLOTS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     delete ctx;
@@ -167,6 +168,19 @@ int mli_ctx_get_option(mli_ctx* ctx, int option, int* value) {
     }
     set_error("unknown option");
     return MLI_ERR_ARG;
+}
+
+int mli_ctx_register_weights(mli_ctx* ctx, const float* wk, const float* wq, const float* wv,
+                             const float* emb_table, int emb_dim, int n_vocab) {
+    MLI_REQUIRE(ctx, "null ctx");
+    if (!ctx->tc_available) return MLI_OK;  // the SIMT path reads the weights in place
+    return tc_register_weights(ctx, wk, wq, wv, emb_table, emb_dim, n_vocab);
+}
+
+int mli_ctx_unregister_weights(mli_ctx* ctx) {
+    MLI_REQUIRE(ctx, "null ctx");
+    if (ctx->tc_available) tc_unregister_all(ctx);
+    return MLI_OK;
 }
 
 int mli_ctx_synchronize(mli_ctx* ctx) {

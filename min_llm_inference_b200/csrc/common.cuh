@@ -85,8 +85,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// Waits in these kernels are bounded by one pipeline stage (microseconds).  A wait that lasts
+// ~2 s can only be a protocol bug; trap so the launch fails loudly instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("mli: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x);
+            __trap();
+        }
     }
 }
 

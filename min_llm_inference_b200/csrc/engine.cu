@@ -609,6 +609,12 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     }
 #undef A
     StreamScope scope(e);
+    // the engine owns the weight lifetime for as long as it lives: split them once (tcgen05 mode)
+    if (ctx->tc_available &&
+        (rc = tc_register_weights(ctx, wk, wq, wv, emb_table, d, V))) {
+        mli_engine_destroy(e);
+        return rc;
+    }
     // zero state so a warm-up step is harmless, then run one un-captured step on the empty engine:
     // it sizes every workspace the captured graph will later hold pointers to.
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(a, e->pool, page_floats, NR);
@@ -625,6 +631,7 @@ int mli_engine_destroy(mli_engine* e) {
     cudaStreamSynchronize(e->ctx->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graph(e);
+    if (e->ctx->tc_available) tc_unregister_weights(e->ctx, e->wk, e->emb);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->join_ev) cudaEventDestroy(e->join_ev);
     for (void* p : e->allocs) cudaFree(p);

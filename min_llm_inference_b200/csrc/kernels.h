@@ -47,6 +47,11 @@ int launch_qkv_latest_dense_simt(mli_ctx* ctx, const float* inp_embedding, const
 
 // ---- tcgen05 3xTF32 GEMMs (gemm_tcgen05.cu) ------------------------------------------------------
 bool tcgen05_supported(mli_ctx* ctx);
+// split/transposed copies of these operands are built once and trusted until unregistered
+int tc_register_weights(mli_ctx* ctx, const float* wk, const float* wq, const float* wv, const float* emb,
+                        int d, int V);
+void tc_unregister_weights(mli_ctx* ctx, const float* wk, const float* emb);
+void tc_unregister_all(mli_ctx* ctx);
 int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const TileDesc* tiles,
                                const int* n_tiles, int max_tiles, const int* lengths,
                                const float* wk, const float* wv, int S, int d);
