@@ -460,6 +460,14 @@ struct StreamScope {
 
 namespace {
 
+// one thread per row up to 1024; fewer warps make the (many) block barriers of the scheduler cheaper
+int sched_threads(int n_batch) {
+    int t = ((n_batch + 31) / 32) * 32;
+    if (t < 128) t = 128;
+    if (t > kSchedThreads) t = kSchedThreads;
+    return t;
+}
+
 template <typename T>
 int dev_alloc(mli_engine* e, T** out, size_t n) {
     void* p = nullptr;
@@ -475,7 +483,7 @@ int enqueue_step(mli_engine* e, bool profile) {
     const mli_engine_cfg& c = e->cfg;
     const int B = c.n_batch, S = c.n_sequence, d = c.emb_dim, V = c.n_vocab;
     int rc;
-    sched_step_kernel<<<1, kSchedThreads, 0, ctx->stream>>>(e->a);
+    sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), 0, ctx->stream>>>(e->a);
     MLI_LAUNCH_CHECK();
     if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0, &e->a.v->n_new, e->tiles,
                                          e->n_tiles, e->max_tiles)))
@@ -715,7 +723,7 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             if (*reinterpret_cast<volatile int*>(e->done_host)) break;
             // lengths as the attention kernel will see them are only known after the scheduler and
             // the latest-QKV stage; rounds > 1 are profiled on the first round's lengths + round
-            sched_step_kernel<<<1, kSchedThreads, 0, ctx->stream>>>(e->a);
+            sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), 0, ctx->stream>>>(e->a);
             MLI_LAUNCH_CHECK();
             MLI_CUDA(cudaMemcpyAsync(e->lengths_host, e->a.lengths, sizeof(int) * (size_t)B,
                                      cudaMemcpyDeviceToHost, ctx->stream));

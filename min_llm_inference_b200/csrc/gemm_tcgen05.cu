@@ -167,12 +167,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     constexpr int kStages = SM::kStages;
     extern __shared__ unsigned char tc_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * BN;
 
     // rows this launch really has (device-side for prefill); uniform early exit before any barrier
     int n_valid = args.n_rows;
     if (args.mode == TC_PREFILL) n_valid = min(n_valid, *args.n_tiles * kTileM);
-    if (n0 >= n_valid) return;
+    if ((int)blockIdx.y * BN >= n_valid) return;
 
     // which features does this CTA produce?
     // LATEST: operand rows are [Wk^T; Wq^T; Wv^T] -> mat 0 = K, 1 = q, 2 = V
@@ -191,7 +190,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + kStages * SM::kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
     float** dst = reinterpret_cast<float**>(base + kStages * SM::kStageBytes + 256);
 
     if (warp == 0 && lane == 0) {
@@ -206,6 +206,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, 128);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr_smem, kChunks * BN);
@@ -216,105 +217,127 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int num_kb = args.K / kBK;
     const int kb_per_chunk = (num_kb + kChunks - 1) / kChunks;
 
+    // Every CTA owns one 128-feature slab and walks the activation tiles nt = blockIdx.y,
+    // blockIdx.y + gridDim.y, ... (the grid is capped at ~2 CTAs per SM so that a launch whose
+    // device-side row count turns out to be tiny does not pay for thousands of empty CTAs).
+    // Pipeline counters run on across tiles; TMEM is handed back and forth with full/empty barriers.
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
-                unsigned char* st = tiles_smem + (size_t)s * SM::kStageBytes;
-                mbar_expect_tx(&full_bar[s], SM::kStageBytes);
-                tma_load_2d(st, &map_a_hi, kb * kBK, m0, &full_bar[s]);
-                tma_load_2d(st + SM::kABytes, &map_a_lo, kb * kBK, m0, &full_bar[s]);
-                tma_load_2d(st + 2 * SM::kABytes, &map_b_hi, kb * kBK, n0, &full_bar[s]);
-                tma_load_2d(st + 2 * SM::kABytes + SM::kBBytes, &map_b_lo, kb * kBK, n0, &full_bar[s]);
+            uint32_t it = 0;
+            for (int nt = blockIdx.y; nt * BN < n_valid; nt += gridDim.y) {
+                const int n0 = nt * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+                    unsigned char* st = tiles_smem + (size_t)s * SM::kStageBytes;
+                    mbar_expect_tx(&full_bar[s], SM::kStageBytes);
+                    tma_load_2d(st, &map_a_hi, kb * kBK, m0, &full_bar[s]);
+                    tma_load_2d(st + SM::kABytes, &map_a_lo, kb * kBK, m0, &full_bar[s]);
+                    tma_load_2d(st + 2 * SM::kABytes, &map_b_hi, kb * kBK, n0, &full_bar[s]);
+                    tma_load_2d(st + 2 * SM::kABytes + SM::kBBytes, &map_b_lo, kb * kBK, n0, &full_bar[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(&full_bar[s], (kb / kStages) & 1);
-                tc_fence_after();
-                unsigned char* st = tiles_smem + (size_t)s * SM::kStageBytes;
-                const uint64_t a_hi = make_kmajor_sw128_desc(st);
-                const uint64_t a_lo = make_kmajor_sw128_desc(st + SM::kABytes);
-                const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * SM::kABytes);
-                const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * SM::kABytes + SM::kBBytes);
-#pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    const uint64_t koff = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 B per k-step
-                    const uint32_t acc = tmem_acc + (uint32_t)((kb / kb_per_chunk) * BN);
-                    umma_tf32(acc, a_lo + koff, b_hi + koff, idesc, ((kb % kb_per_chunk) | k) != 0);
-                    umma_tf32(acc, a_hi + koff, b_lo + koff, idesc, 1);
-                    umma_tf32(acc, a_hi + koff, b_hi + koff, idesc, 1);
+            uint32_t it = 0, tile_iter = 0;
+            for (int nt = blockIdx.y; nt * BN < n_valid; nt += gridDim.y, ++tile_iter) {
+                if (tile_iter > 0) {   // epilogue must have drained the accumulators of the last tile
+                    mbar_wait(tmem_empty_bar, (tile_iter - 1) & 1);
+                    tc_fence_after();
                 }
-                umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&full_bar[s], (it / kStages) & 1);
+                    tc_fence_after();
+                    unsigned char* st = tiles_smem + (size_t)s * SM::kStageBytes;
+                    const uint64_t a_hi = make_kmajor_sw128_desc(st);
+                    const uint64_t a_lo = make_kmajor_sw128_desc(st + SM::kABytes);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * SM::kABytes);
+                    const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * SM::kABytes + SM::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint64_t koff = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 B per k-step
+                        const uint32_t acc = tmem_acc + (uint32_t)((kb / kb_per_chunk) * BN);
+                        umma_tf32(acc, a_lo + koff, b_hi + koff, idesc, ((kb % kb_per_chunk) | k) != 0);
+                        umma_tf32(acc, a_hi + koff, b_lo + koff, idesc, 1);
+                        umma_tf32(acc, a_hi + koff, b_hi + koff, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
+                }
+                umma_commit(tmem_full_bar);       // accumulators of this tile complete
             }
-            umma_commit(tmem_full_bar);       // accumulator complete
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int et = threadIdx.x - 128;  // 0..127
-        // destination of activation row n0 + i (base pointer for this CTA's feature range)
-        for (int i = et; i < BN; i += 128) {
-            const int n = n0 + i;
-            float* p = nullptr;
-            if (n < n_valid) {
-                if (args.mode == TC_LOGITS) {
-                    p = args.score + (size_t)n * args.V + f0;
-                } else {
-                    int r, j;
-                    bool ok;
-                    if (args.mode == TC_LATEST) {
-                        r = n;
-                        const int L = args.lengths[r];
-                        j = L - 1;
-                        ok = L > 0;
+        const int ew = warp - 4;           // TMEM lane quadrant of this warp
+        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+        const int n_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
+        uint32_t tile_iter = 0;
+        for (int nt = blockIdx.y; nt * BN < n_valid; nt += gridDim.y, ++tile_iter) {
+            const int n0 = nt * BN;
+            named_bar_sync(1, 128);   // previous tile's stores no longer read dst[]
+            // destination of activation row n0 + i (base pointer for this CTA's feature range)
+            for (int i = et; i < BN; i += 128) {
+                const int n = n0 + i;
+                float* p = nullptr;
+                if (n < n_valid) {
+                    if (args.mode == TC_LOGITS) {
+                        p = args.score + (size_t)n * args.V + f0;
                     } else {
-                        const TileDesc t = args.tiles[n / kTileM];
-                        r = t.row;
-                        j = t.j0 + (n % kTileM);
-                        ok = j < args.lengths[r];
-                    }
-                    if (ok) {
-                        if (mat == 1) {
-                            p = args.q_out + (size_t)r * args.d + f0;
+                        int r, j;
+                        bool ok;
+                        if (args.mode == TC_LATEST) {
+                            r = n;
+                            const int L = args.lengths[r];
+                            j = L - 1;
+                            ok = L > 0;
                         } else {
-                            float* page = args.page_table[(size_t)r * args.W + j / kPage];
-                            p = page_row_ptr(page, j, args.d, mat == 0 ? 1 : 2) + f0;
+                            const TileDesc t = args.tiles[n / kTileM];
+                            r = t.row;
+                            j = t.j0 + (n % kTileM);
+                            ok = j < args.lengths[r];
+                        }
+                        if (ok) {
+                            if (mat == 1) {
+                                p = args.q_out + (size_t)r * args.d + f0;
+                            } else {
+                                float* page = args.page_table[(size_t)r * args.W + j / kPage];
+                                p = page_row_ptr(page, j, args.d, mat == 0 ? 1 : 2) + f0;
+                            }
                         }
                     }
                 }
+                dst[i] = p;
             }
-            dst[i] = p;
-        }
-        named_bar_sync(1, 128);
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const int ew = warp - 4;                       // TMEM lane quadrant of this warp
-        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+            named_bar_sync(1, 128);
+            mbar_wait(tmem_full_bar, tile_iter & 1);
+            tc_fence_after();
 #pragma unroll 1
-        const int n_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_acc + lane_base + (uint32_t)c0, v);
-            for (int ch = 1; ch < n_chunks; ++ch) {
-                float u[32];
-                tmem_ld32(tmem_acc + lane_base + (uint32_t)(ch * BN + c0), u);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_acc + lane_base + (uint32_t)c0, v);
+                for (int ch = 1; ch < n_chunks; ++ch) {
+                    float u[32];
+                    tmem_ld32(tmem_acc + lane_base + (uint32_t)(ch * BN + c0), u);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += u[j];
-            }
+                    for (int j = 0; j < 32; ++j) v[j] += u[j];
+                }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float* p = dst[c0 + j];
-                if (p != nullptr) p[ew * 32 + lane] = v[j];   // 32 lanes -> 128 contiguous bytes
+                for (int j = 0; j < 32; ++j) {
+                    float* p = dst[c0 + j];
+                    if (p != nullptr) p[ew * 32 + lane] = v[j];   // 32 lanes -> 128 contiguous bytes
+                }
             }
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar);   // accumulators may be overwritten by the next tile
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -574,7 +597,11 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, const float* dens
     if (ggrid > ctx->num_sms * 8) ggrid = ctx->num_sms * 8;
     gather_split_rows_kernel<<<ggrid, 256, 0, ctx->stream>>>(args, dense_src, hi, lo);
     MLI_LAUNCH_CHECK();
-    dim3 grid(m_tiles, (unsigned)((rows + bn - 1) / bn));
+    // cap the grid at ~2 CTAs per SM; CTAs walk the remaining activation tiles themselves
+    unsigned ny = (unsigned)((rows + bn - 1) / bn);
+    const unsigned cap = (unsigned)((2 * ctx->num_sms + m_tiles - 1) / m_tiles);
+    if (ny > cap) ny = cap;
+    dim3 grid(m_tiles, ny);
     return bn64 ? launch_tc<64>(ctx, w, mh, ml, grid, args) : launch_tc<128>(ctx, w, mh, ml, grid, args);
 }
 

@@ -54,7 +54,8 @@ def test_logits(torch_cuda, tc, ref, B, V, d, dist):
     assert np.array_equal(outs[0][1], outs[1][1]), "tokens differ between tcgen05 and exact mode"
 
 
-@pytest.mark.parametrize("B,S,d", [(8, 64, 128), (33, 128, 256), (256, 128, 1024), (40, 256, 2048)])
+@pytest.mark.parametrize("B,S,d", [(8, 64, 128), (33, 128, 256), (256, 128, 1024), (40, 256, 2048),
+                                   (48, 1024, 128)])   # last: more activation tiles than the grid cap
 @pytest.mark.parametrize("dist", ["R", "Z"])
 @pytest.mark.parametrize("registered", [False, True])
 def test_latest_and_prefill(torch_cuda, tc, ref, B, S, d, dist, registered):
@@ -67,7 +68,7 @@ def test_latest_and_prefill(torch_cuda, tc, ref, B, S, d, dist, registered):
     case = H.PagedCase(7, B, S, d, L, dist)
     w = H.make_weights(11, d, V, S, dist)
     cand = np.flatnonzero(L > 0)
-    n_new = max(1, len(cand) // 2)
+    n_new = max(1, len(cand) // 2) if S < 1024 else len(cand)
     new_idx = np.zeros(B, np.int32)
     new_idx[:n_new] = rng.permutation(cand)[:n_new]
     dw = {k: dev(torch, v) for k, v in w.items()}
