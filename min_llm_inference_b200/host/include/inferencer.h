@@ -1,0 +1,3 @@
+// drop-in name of the reference header include/inferencer.h; everything lives in mli/compat.hpp
+#pragma once
+#include "mli/compat.hpp"

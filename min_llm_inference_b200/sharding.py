@@ -1,0 +1,39 @@
+"""Request-level data parallelism: a request only ever touches its own row state and KV
+pages, so ranks are fully independent -- each owns a slab, a page table and a device scheduler.  The
+one collective of the path is the final token gather (NCCL all-gather over NVLink on GPUs; the same
+code runs on gloo for the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_requests(offsets: np.ndarray, tokens: np.ndarray, rank: int, world: int):
+    """contiguous block of requests for `rank`; returns (local offsets, local tokens, global ids)"""
+    n = len(offsets) - 1
+    per = (n + world - 1) // world
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    local_offs = (offsets[lo:hi + 1] - offsets[lo]).astype(np.int32)
+    local_toks = tokens[offsets[lo]:offsets[hi]].astype(np.int32)
+    return local_offs, local_toks, np.arange(lo, hi, dtype=np.int64)
+
+
+def gather_tokens(local_tokens, local_counts, n_total: int):
+    """all-gather the per-rank request tables [n_local, S] (+ counts) into [n_total, S] on every rank.
+    local_* are torch tensors on the backend's device; ranks may hold unequal request counts."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return local_tokens[:n_total], local_counts[:n_total]
+    per = (n_total + world - 1) // world
+    S = local_tokens.shape[1]
+    pad_t = torch.zeros((per, S), dtype=local_tokens.dtype, device=local_tokens.device)
+    pad_c = torch.zeros((per,), dtype=local_counts.dtype, device=local_counts.device)
+    pad_t[:local_tokens.shape[0]] = local_tokens
+    pad_c[:local_counts.shape[0]] = local_counts
+    all_t = torch.empty((world * per, S), dtype=local_tokens.dtype, device=local_tokens.device)
+    all_c = torch.empty((world * per,), dtype=local_counts.dtype, device=local_counts.device)
+    dist.all_gather_into_tensor(all_t, pad_t)
+    dist.all_gather_into_tensor(all_c, pad_c)
+    return all_t[:n_total], all_c[:n_total]
