@@ -281,9 +281,12 @@ def main():
         ctx.set_option(mli.OPT_GEMM_MODE, args.gemm_mode)
     gemm_mode = ctx.get_option(mli.OPT_GEMM_MODE)
 
-    # same weights on every rank (replicated; each rank regenerates them from the seed), its own requests
+    # weights are replicated (every rank regenerates them from the seed); the global request set is
+    # n_req * world requests from one seed, sharded by contiguous blocks (weak scaling)
+    from min_llm_inference_b200.sharding import gather_tokens, shard_requests
     w = H.make_weights(1001, d, V, S, "Z")
-    offs, toks = H.make_prompts(2002 + rank, wl["n_req"], wl["lo"], wl["hi"])
+    g_offs, g_toks = H.make_prompts(2002, wl["n_req"] * world, wl["lo"], wl["hi"])
+    offs, toks, _ = shard_requests(g_offs, g_toks, rank, world)
     dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
     ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None)
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
@@ -292,7 +295,6 @@ def main():
     p_toks = torch.from_numpy(toks).pin_memory()
     tok_buf = torch.zeros((wl["n_req"], S), dtype=torch.int32, device="cuda")
     cnt_buf = torch.zeros((wl["n_req"],), dtype=torch.int32, device="cuda")
-    gather_tok = torch.zeros((world, wl["n_req"], S), dtype=torch.int32, device="cuda") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -309,7 +311,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             eng.copy_tokens(tok_buf, cnt_buf)
-            dist.all_gather_into_tensor(gather_tok.view(-1), tok_buf.view(-1))
+            gather_tokens(tok_buf, cnt_buf, wl["n_req"] * world)
             e1.record()
             torch.cuda.synchronize()
             ms += e0.elapsed_time(e1)
