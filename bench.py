@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference CUDA / long-context legs")
+    ap.add_argument("--pdl", type=int, default=-1, help="override MLI_OPT_PDL (1 programmatic dependent launch, 0 off)")
     ap.add_argument("--gemm-mode", type=int, default=-1, help="override MLI_OPT_GEMM_MODE (0 tcgen05, 1 SIMT exact)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -282,6 +283,8 @@ def main():
     if args.gemm_mode >= 0:
         ctx.set_option(mli.OPT_GEMM_MODE, args.gemm_mode)
     gemm_mode = ctx.get_option(mli.OPT_GEMM_MODE)
+    if args.pdl >= 0:
+        ctx.set_option(mli.OPT_PDL, args.pdl)
 
     # weights are replicated (every rank regenerates them from the seed); the global request set is
     # n_req * world requests from one seed, sharded by contiguous blocks (weak scaling)
@@ -382,6 +385,7 @@ def main():
                        "kv_pages": wl["n_blocks"], "requests_per_gpu": wl["n_req"], "n_forward_rounds": 1,
                        "distribution": "Z (zero-mean), fixed seeds", "lengths": "corrected (no Q1 replay)",
                        "gemm_mode": "tcgen05 3xTF32" if gemm_mode == 0 else "SIMT fp32 exact-order",
+                       "pdl": ctx.get_option(mli.OPT_PDL),
                        "l2": "inputs larger than L2 (KV pool 201 MB + tables > 126 MB); no flush",
                        "parallelism": f"request-sharded dp{world}",
                        "step": "one whole engine job (512 requests per GPU to completion)"},

@@ -50,7 +50,10 @@ typedef enum {
                                          available), 1 = SIMT fp32 with the reference's k-ascending
                                          FMA order (bit-exact with the reference's naive kernels) */
     MLI_OPT_ATTN_CHUNK_PAGES = 2, /* KV pages per split of the fused decode attention; 0 = auto */
-    MLI_OPT_ATTN_CTAS_PER_SM = 3  /* persistent CTAs per SM for the fused decode attention; 0 = auto */
+    MLI_OPT_ATTN_CTAS_PER_SM = 3, /* persistent CTAs per SM for the fused decode attention; 0 = auto */
+    MLI_OPT_PDL = 4               /* 1 (default) = the engine's step graph chains its kernels with
+                                         programmatic dependent launch (each kernel's prologue overlaps
+                                         the tail of its predecessor); 0 = plain stream order */
 } mli_option;
 
 /* ---- context --------------------------------------------------------------------------- */
@@ -71,6 +74,9 @@ const char* mli_last_error(void);
 const char* mli_version(void);
 /* number of kernels this library has launched in this process (bench.py reports it) */
 long long mli_kernel_launch_count(void);
+/* diagnostics (tools/gemm_timing.py): when stamps_dev != NULL every tcgen05 GEMM launch writes
+ * clock64() phase stamps [cta][8] into it (>= 8 * 8 * n_ctas bytes); NULL switches it off */
+int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev);
 
 /* ---- paged stages ------------------------------------------------------------------------ */
 /* replaces launch_paged_attention_encoder_kernel (include/kernels/encoder.h:21-25,

@@ -18,6 +18,7 @@ LIB_PATH = PKG_DIR / "libmli_b200.so"
 OPT_GEMM_MODE = 1
 OPT_ATTN_CHUNK_PAGES = 2
 OPT_ATTN_CTAS_PER_SM = 3
+OPT_PDL = 4
 GEMM_TCGEN05 = 0
 GEMM_SIMT_EXACT = 1
 
@@ -58,6 +59,7 @@ SIGNATURES = {
     "mli_last_error": (C.c_char_p, []),
     "mli_version": (C.c_char_p, []),
     "mli_kernel_launch_count": (_LL, []),
+    "mli_debug_set_gemm_stamps": (_I, [_P, _P]),
     "mli_paged_encoder": (_I, [_P] * 7 + [_I] * 4),
     "mli_prefill_kv_paged": (_I, [_P] * 6 + [_I] * 4),
     "mli_qkv_latest_paged": (_I, [_P] * 7 + [_I] * 3),

@@ -44,6 +44,15 @@ int ws_get(mli_ctx* ctx, int slot, size_t bytes, void** out) {
     return 0;
 }
 
+int ws_get_zeroed(mli_ctx* ctx, int slot, size_t bytes, void** out) {
+    const size_t had = ctx->ws_bytes[slot];
+    int rc = ws_get(ctx, slot, bytes, out);
+    if (rc) return rc;
+    if (ctx->ws_bytes[slot] != had)
+        MLI_CUDA(cudaMemsetAsync(ctx->ws[slot], 0, ctx->ws_bytes[slot], ctx->stream));
+    return 0;
+}
+
 static bool use_tc(mli_ctx* ctx) { return ctx->gemm_mode == 0 && ctx->tc_available; }
 
 // tile-list workspace: [int n_tiles | pad to 16 B | TileDesc tiles[max_tiles]]
@@ -154,6 +163,10 @@ int mli_ctx_set_option(mli_ctx* ctx, int option, int value) {
             MLI_REQUIRE(value >= 0 && value <= 2, "CTAs per SM must be in [0,2]");
             ctx->attn_ctas_per_sm = value;
             return MLI_OK;
+        case MLI_OPT_PDL:
+            MLI_REQUIRE(value == 0 || value == 1, "pdl must be 0 or 1");
+            ctx->opt_pdl = value;
+            return MLI_OK;
     }
     set_error("unknown option");
     return MLI_ERR_ARG;
@@ -165,6 +178,7 @@ int mli_ctx_get_option(mli_ctx* ctx, int option, int* value) {
         case MLI_OPT_GEMM_MODE: *value = ctx->gemm_mode; return MLI_OK;
         case MLI_OPT_ATTN_CHUNK_PAGES: *value = ctx->attn_chunk_pages; return MLI_OK;
         case MLI_OPT_ATTN_CTAS_PER_SM: *value = ctx->attn_ctas_per_sm; return MLI_OK;
+        case MLI_OPT_PDL: *value = ctx->opt_pdl; return MLI_OK;
     }
     set_error("unknown option");
     return MLI_ERR_ARG;
@@ -180,6 +194,12 @@ int mli_ctx_register_weights(mli_ctx* ctx, const float* wk, const float* wq, con
 int mli_ctx_unregister_weights(mli_ctx* ctx) {
     MLI_REQUIRE(ctx, "null ctx");
     if (ctx->tc_available) tc_unregister_all(ctx);
+    return MLI_OK;
+}
+
+int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev) {
+    MLI_REQUIRE(ctx, "null ctx");
+    ctx->tc_dbg = stamps_dev;
     return MLI_OK;
 }
 

@@ -120,6 +120,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// programmatic dependent launch: everything before griddep_wait() may overlap the tail of the
+// previous kernel in the stream; nothing that kernel wrote may be read before it.  Both are no-ops
+// for a kernel launched without the attribute.  EVERY kernel of a PDL chain must execute the wait
+// on every path (completion of a kernel must imply completion of its predecessors).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -135,6 +144,7 @@ namespace mli {
 enum WsSlot {
     WS_ATTN_META = 0,  // item lists / per-row prefix for the fused attention
     WS_ATTN_PART,      // split-KV partial accumulators
+    WS_ATTN_CNT,       // per-row arrival counters of the fused attention (zero between launches)
     WS_TILES,          // M-tile lists for prefill / encoder
     WS_LOGITS,         // [B,V] logits when the caller does not want them
     WS_QOUT,           // q_output when the caller passes NULL
@@ -156,6 +166,9 @@ struct mli_ctx {
     int attn_ctas_per_sm = 0;   // 0 = auto
     void* ws[mli::WS_NUM_SLOTS] = {};
     size_t ws_bytes[mli::WS_NUM_SLOTS] = {};
+    void* tc_dbg = nullptr;     // device buffer for GEMM phase stamps (tools/gemm_timing.py), else NULL
+    int opt_pdl = 1;            // MLI_OPT_PDL
+    bool use_pdl = false;       // launch_kernel() adds programmatic stream serialization (set by the engine)
     bool ws_frozen = false;     // set while a CUDA graph that captured ws pointers is alive
     // when set, the fused decode-attention main kernel is bracketed by these events (profiling)
     cudaEvent_t attn_ev_start = nullptr, attn_ev_stop = nullptr;
@@ -165,4 +178,26 @@ namespace mli {
 // device buffer of at least `bytes` for `slot` (grows with a synchronous re-allocation; growing
 // while frozen is an error because captured graphs hold the old pointer)
 int ws_get(mli_ctx* ctx, int slot, size_t bytes, void** out);
+// same, and the buffer is zero-filled whenever it is (re)allocated
+int ws_get_zeroed(mli_ctx* ctx, int slot, size_t bytes, void** out);
+
+// launch on the context's stream; with ctx->use_pdl the kernel is allowed to start while its
+// predecessor drains (programmatic dependent launch) -- only for kernels that call griddep_wait()
+// before touching anything a predecessor produces or still reads
+template <typename... KArgs, typename... Args>
+int launch_kernel(mli_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+    MLI_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    count_launch();
+    return 0;
+}
 }  // namespace mli

@@ -89,14 +89,21 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-template <int NC, int G>
+// FUSED = true: the item list is derived inside the kernel (every CTA scans the lengths into a
+// shared-memory prefix; B <= kMaxFusedRows) and split partials are merged by whichever CTA finishes
+// a row's last chunk (per-row arrival counter in global memory, self-resetting) -- ONE launch per
+// decode step.  FUSED = false: item list from attn_prep_kernel, merge by attn_combine_kernel (used
+// when the [B,S] probabilities are requested or B is too large for the shared-memory prefix).
+constexpr int kMaxFusedRows = 4096;
+
+template <int NC, int G, bool FUSED>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ page_table,
-                        const int* __restrict__ lengths, const int* __restrict__ row_first,
+                        const int* __restrict__ lengths, const int* __restrict__ row_first_g,
                         const int* __restrict__ item_row, const int* __restrict__ item_chunk,
                         float* __restrict__ out, float* __restrict__ part_acc,
-                        float* __restrict__ part_ml, float* __restrict__ scores_out, int B, int S,
-                        int d, int chunk_pages, int nstage) {
+                        float* __restrict__ part_ml, float* __restrict__ scores_out,
+                        int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = S / kPage;
     const int d4 = d >> 2;
@@ -106,10 +113,11 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_floats);
     uint64_t* empty_bar = full_bar + kMaxStages;
     float* red = reinterpret_cast<float*>(empty_bar + kMaxStages);  // [2][kConsumerWarps][G]
+    int* scan_tmp = reinterpret_cast<int*>(red + 2 * kConsumerWarps * G);   // [16]: warp totals, carry, flag
+    int* row_first_s = scan_tmp + 16;                                        // FUSED: [B + 1]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int n_items = row_first[B];
     const int chunk_pos = chunk_pages * kPage;
 
     if (tid == 0) {
@@ -120,13 +128,61 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         mbar_fence_init();
     }
     __syncthreads();
+    griddep_wait();
+    griddep_launch_dependents();
+
+    int n_items;
+    if constexpr (FUSED) {
+        // exclusive prefix of chunk counts over the rows, kAttnThreads rows at a time
+        if (tid == 0) scan_tmp[12] = 0;
+        __syncthreads();
+        for (int base = 0; base < B; base += kAttnThreads) {
+            const int r = base + tid;
+            const int L = (r < B) ? lengths[r] : 0;
+            const int n = (L + chunk_pos - 1) / chunk_pos;
+            int v = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (lane == 31) scan_tmp[warp] = v;
+            __syncthreads();
+            int before = scan_tmp[12];
+            for (int w = 0; w < warp; ++w) before += scan_tmp[w];
+            if (r < B) row_first_s[r] = before + v - n;
+            __syncthreads();
+            if (tid == kAttnThreads - 1) scan_tmp[12] = before + v;
+            __syncthreads();
+        }
+        n_items = scan_tmp[12];
+        if (tid == 0) row_first_s[B] = n_items;
+        __syncthreads();
+    } else {
+        n_items = row_first_g[B];
+    }
+    // item -> (row, chunk)
+    auto locate = [&](int item, int& r, int& c) {
+        if constexpr (FUSED) {
+            int lo = 0, hi = B;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (row_first_s[mid] <= item) lo = mid; else hi = mid;
+            }
+            r = lo;
+            c = item - row_first_s[lo];
+        } else {
+            r = item_row[item];
+            c = item_chunk[item];
+        }
+    };
 
     if (warp == kConsumerWarps) {
         // ===================== producer warp =====================
         uint32_t it = 0;  // running stage counter across items
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int r = item_row[item];
-            const int c = item_chunk[item];
+            int r, c;
+            locate(item, r, c);
             const int L = lengths[r];
             const int p0 = c * chunk_pos;
             const int p1 = min(L, p0 + chunk_pos);
@@ -159,13 +215,19 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     }
 
     // ===================== consumer warps =====================
-    const float inv_dummy = 0.f;
-    (void)inv_dummy;
     const float sqrt_d = sqrtf((float)d);
+    if constexpr (FUSED) {
+        // empty rows produce zeros (the reference stores result = 0, paged_attention.cu:289,:323)
+        for (int r = blockIdx.x; r < B; r += gridDim.x) {
+            if (lengths[r] != 0) continue;
+            for (int col = tid; col < d4; col += kConsumerThreads)
+                reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int r = item_row[item];
-        const int c = item_chunk[item];
+        int r, c;
+        locate(item, r, c);
         const int L = lengths[r];
         const int p0 = c * chunk_pos;
         const int p1 = min(L, p0 + chunk_pos);
@@ -263,11 +325,11 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         }
 
         // ---- item epilogue ----
-        if (tid == 0) {
-            part_ml[2 * (size_t)item] = m_run;
-            part_ml[2 * (size_t)item + 1] = l_run;
-        }
         if (nchunks == 1) {
+            if (!FUSED && tid == 0) {
+                part_ml[2 * (size_t)item] = m_run;
+                part_ml[2 * (size_t)item + 1] = l_run;
+            }
             const float norm = 1.f / l_run;
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
@@ -277,10 +339,47 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         acc[i].x * norm, acc[i].y * norm, acc[i].z * norm, acc[i].w * norm);
             }
         } else {
+            if (tid == 0) {
+                part_ml[2 * (size_t)item] = m_run;
+                part_ml[2 * (size_t)item + 1] = l_run;
+            }
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 const int col = tid + i * kConsumerThreads;
                 if (col < d4) reinterpret_cast<float4*>(part_acc + (size_t)item * d)[col] = acc[i];
+            }
+            if constexpr (FUSED) {
+                // whoever completes the row's last chunk merges the partials
+                __threadfence();
+                named_bar_sync(1, kConsumerThreads);
+                if (tid == 0) scan_tmp[13] = (atomicAdd(&row_done[r], 1) == nchunks - 1) ? 1 : 0;
+                named_bar_sync(1, kConsumerThreads);
+                if (scan_tmp[13]) {
+                    __threadfence();
+                    const size_t first = (size_t)(item - c);
+                    float M = -INFINITY;
+                    for (int i = 0; i < nchunks; ++i) M = fmaxf(M, __ldcg(part_ml + 2 * (first + i)));
+                    float Lsum = 0.f;
+                    for (int i = 0; i < nchunks; ++i)
+                        Lsum += __ldcg(part_ml + 2 * (first + i) + 1) * expf(__ldcg(part_ml + 2 * (first + i)) - M);
+                    const float norm = 1.f / Lsum;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int col = tid + i * kConsumerThreads;
+                        if (col < d4) {
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int k = 0; k < nchunks; ++k) {
+                                const float w = expf(__ldcg(part_ml + 2 * (first + k)) - M);
+                                const float4 p = __ldcg(reinterpret_cast<const float4*>(part_acc + (first + k) * d) + col);
+                                a.x = fmaf(w, p.x, a.x); a.y = fmaf(w, p.y, a.y);
+                                a.z = fmaf(w, p.z, a.z); a.w = fmaf(w, p.w, a.w);
+                            }
+                            reinterpret_cast<float4*>(out + (size_t)r * d)[col] =
+                                make_float4(a.x * norm, a.y * norm, a.z * norm, a.w * norm);
+                        }
+                    }
+                    if (tid == 0) row_done[r] = 0;   // ready for the next launch
+                }
             }
         }
     }
@@ -361,7 +460,7 @@ static int plan_attention(mli_ctx* ctx, int B, int S, int d, AttnPlan* p) {
     if (nstage > kMaxStages) nstage = kMaxStages;
     p->nstage = nstage;
     p->smem = nstage * stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
-              2 * kConsumerWarps * G * sizeof(float) + 128;
+              2 * kConsumerWarps * G * sizeof(float) + 16 * sizeof(int) + 128;
     int ch = ctx->attn_chunk_pages;
     if (ch <= 0) {
         // aim for a few items per persistent CTA without making items tiny
@@ -384,23 +483,23 @@ size_t attention_meta_bytes(int B, int max_items) {
     return sizeof(int) * ((size_t)B + 1 + 2 * (size_t)max_items + 8);
 }
 
-template <int NC, int G>
+template <int NC, int G, bool FUSED>
 static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* const* page_table,
                        const int* lengths, const int* row_first, const int* item_row,
                        const int* item_chunk, float* out, float* part_acc, float* part_ml,
-                       float* scores_out, int B, int S, int d) {
-    auto kern = decode_attention_kernel<NC, G>;
+                       float* scores_out, int* row_done, int B, int S, int d) {
+    auto kern = decode_attention_kernel<NC, G, FUSED>;
+    const size_t smem = p.smem + (FUSED ? sizeof(int) * ((size_t)B + 1) : 0);
     static size_t configured = 0;  // per instantiation
-    if (configured < p.smem) {
-        MLI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        configured = p.smem;
+    if (configured < smem) {
+        MLI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
-    kern<<<p.grid, kAttnThreads, p.smem, ctx->stream>>>(q, page_table, lengths, row_first, item_row,
-                                                         item_chunk, out, part_acc, part_ml,
-                                                         scores_out, B, S, d, p.chunk_pages,
-                                                         p.nstage);
-    MLI_LAUNCH_CHECK();
+    int rc = launch_kernel(ctx, kern, dim3(p.grid), dim3(kAttnThreads), smem, q, page_table, lengths,
+                           row_first, item_row, item_chunk, out, part_acc, part_ml, scores_out, row_done,
+                           B, S, d, p.chunk_pages, p.nstage);
+    if (rc) return rc;
     if (ctx->attn_ev_stop) MLI_CUDA(cudaEventRecord(ctx->attn_ev_stop, ctx->stream));
     return 0;
 }
@@ -411,28 +510,39 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     AttnPlan p;
     int rc = plan_attention(ctx, B, S, d, &p);
     if (rc) return rc;
+    const bool fused = (softmax_out == nullptr) && B <= kMaxFusedRows;
     void* meta = nullptr;
     void* part = nullptr;
+    void* cnt = nullptr;
     rc = ws_get(ctx, WS_ATTN_META, attention_meta_bytes(B, p.max_items), &meta);
     if (rc) return rc;
     rc = ws_get(ctx, WS_ATTN_PART, sizeof(float) * ((size_t)p.max_items * (d + 2) + 8), &part);
     if (rc) return rc;
+    rc = ws_get_zeroed(ctx, WS_ATTN_CNT, sizeof(int) * (size_t)B, &cnt);
+    if (rc) return rc;
     int* row_first = reinterpret_cast<int*>(meta);
     int* item_row = row_first + B + 1;
     int* item_chunk = item_row + p.max_items;
+    int* row_done = reinterpret_cast<int*>(cnt);
     float* part_ml = reinterpret_cast<float*>(part);
     float* part_acc = part_ml + 2 * (size_t)p.max_items;
     // keep part_acc 16-byte aligned
     part_acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(part_acc) + 15) & ~(uintptr_t)15);
 
-    attn_prep_kernel<<<1, 1024, 0, ctx->stream>>>(lengths, B, p.chunk_pages * kPage, row_first,
-                                                   item_row, item_chunk);
-    MLI_LAUNCH_CHECK();
+    if (!fused) {
+        attn_prep_kernel<<<1, 1024, 0, ctx->stream>>>(lengths, B, p.chunk_pages * kPage, row_first,
+                                                       item_row, item_chunk);
+        MLI_LAUNCH_CHECK();
+    }
 
-#define MLI_ATTN_CASE(NC_, G_)                                                                   \
-    if (p.NC == NC_ && p.G == G_)                                                                \
-        rc = launch_main<NC_, G_>(p, ctx, q, page_table, lengths, row_first, item_row, item_chunk, \
-                                  out, part_acc, part_ml, softmax_out, B, S, d);                 \
+#define MLI_ATTN_CASE(NC_, G_)                                                                       \
+    if (p.NC == NC_ && p.G == G_)                                                                    \
+        rc = fused ? launch_main<NC_, G_, true>(p, ctx, q, page_table, lengths, row_first, item_row, \
+                                                item_chunk, out, part_acc, part_ml, softmax_out,     \
+                                                row_done, B, S, d)                                   \
+                   : launch_main<NC_, G_, false>(p, ctx, q, page_table, lengths, row_first, item_row, \
+                                                 item_chunk, out, part_acc, part_ml, softmax_out,    \
+                                                 row_done, B, S, d);                                 \
     else
     MLI_ATTN_CASE(1, 16)
     MLI_ATTN_CASE(1, 8)
@@ -447,9 +557,11 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
 #undef MLI_ATTN_CASE
     if (rc) return rc;
 
-    attn_combine_kernel<<<B, 256, 0, ctx->stream>>>(lengths, row_first, part_acc, part_ml, out,
-                                                    softmax_out, S, d);
-    MLI_LAUNCH_CHECK();
+    if (!fused) {
+        attn_combine_kernel<<<B, 256, 0, ctx->stream>>>(lengths, row_first, part_acc, part_ml, out,
+                                                        softmax_out, S, d);
+        MLI_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     const int tid = threadIdx.x, T = blockDim.x;
     SchedVars* v = a.v;
     const int B = a.B, S = a.S, W = a.W, R = a.R;
+    griddep_wait();
+    griddep_launch_dependents();
 
     if (v->done) {
         __syncthreads();
@@ -483,8 +485,16 @@ int enqueue_step(mli_engine* e, bool profile) {
     const mli_engine_cfg& c = e->cfg;
     const int B = c.n_batch, S = c.n_sequence, d = c.emb_dim, V = c.n_vocab;
     int rc;
+    // the scheduler is the head of the step: plain launch (fully ordered after the previous step);
+    // everything after it may be chained with programmatic dependent launch
+    struct PdlScope {
+        mli_ctx* c;
+        explicit PdlScope(mli_ctx* c_) : c(c_) { c->use_pdl = c->opt_pdl != 0; }
+        ~PdlScope() { c->use_pdl = false; }
+    };
     sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), 0, ctx->stream>>>(e->a);
     MLI_LAUNCH_CHECK();
+    PdlScope pdl(ctx);
     if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0, &e->a.v->n_new, e->tiles,
                                          e->n_tiles, e->max_tiles)))
         return rc;

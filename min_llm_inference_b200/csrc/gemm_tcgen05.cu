@@ -4,29 +4,28 @@
 // All three are  D[f, n] = sum_k W[f, k] * X[n, k]  with
 //     f  = output feature (rows of the K-major, pre-transposed weight matrix [Wk^T; Wq^T; Wv^T],
 //          or rows of emb_table for the logits)           -> UMMA M = 128 (TMEM lanes)
-//     n  = activation row (batch row / prompt position)   -> UMMA N = 64 or 128 (TMEM columns)
+//     n  = activation row (batch row / prompt position)   -> UMMA N = 16..256 (TMEM columns)
 //     k  = emb_dim                                        -> 32 floats (= one 128-byte swizzle row)
 //          per pipeline stage, UMMA_K = 8 for tf32
 // "swap-AB": the (small, ragged) batch dimension is the MMA N, so decode batches of any size fill
 // the 128-lane accumulator.  Inputs are fp32; the tensor cores take tf32, so every operand is
 // split  x = hi + lo  (hi = rna_tf32(x), lo = rna_tf32(x - hi)) and each k-step issues three
-// MMAs, hi*hi + lo*hi + hi*lo, into ONE fp32 accumulator in TMEM (3xTF32; relative error ~5e-7,
+// MMAs, hi*hi + lo*hi + hi*lo, into an fp32 accumulator in TMEM (3xTF32; relative error ~5e-7,
 // against 4.9e-4 for plain tf32 -- SURVEY App. C).  Weights are split/transposed once per
-// registered weight set; activations by a gather-and-split pass that reads the page rows.
-//
-// Kernel anatomy (one CTA per 128 x BN output tile, 256 threads):
-//   warp 0  one elected lane: TMA producer (cp.async.bulk.tensor.2d, 128B swizzle, 4 tiles/stage)
-//   warp 1  one elected lane: tcgen05.mma.cta_group::1.kind::tf32 issuer, tcgen05.commit -> mbarriers
-//   warp 2  TMEM allocator (tcgen05.alloc / dealloc)
-//   warps 4-7  epilogue: tcgen05.ld 32x32b -> registers -> coalesced stores straight into the KV
-//              pages / q_output / logits (the reference's save_to_page_table scatter,
-//              src/kernels/paged_attention_cublas.cu:45-67, fused into the GEMM)
+// registered weight set and arrive by TMA; activation rows are gathered from the KV pages and split
+// inside the kernel (no staging pass through HBM).  At decode sizes these GEMMs are bound by the
+// operand bytes one SM can ingest, so the tile is 128 features x up to 256 rows (weights read once
+// per 256 rows) and K is split across a thread-block cluster whose partial tiles are summed
+// through distributed shared memory in a fixed order.  The epilogue writes straight into the KV
+// pages / q_output / logits (the reference's gather + 3 sgemm + save_to_page_table scatter,
+// src/kernels/paged_attention_cublas.cu:45-99, is one kernel).
 #include "common.cuh"
 #include "kernels.h"
 
 #include <cuda.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -38,11 +37,10 @@ namespace {
 constexpr int kBM = 128;       // features per tile (TMEM lanes)
 constexpr int kBK = 32;        // fp32 per stage row = 128 B = one swizzle row
 constexpr int kUmmaK = 8;      // tf32 MMA K
-constexpr int kTcThreads = 256;
 // The tensor core adds each MMA into the fp32 accumulator with truncation, so one long chain over
 // K drifts by ~K/16 ulp (measured 2.4e-5 relative at K = 2048 on all-positive data).  The K loop is
-// therefore cut into kChunks accumulators in TMEM which the epilogue adds with ordinary fp32 adds.
-constexpr int kChunks = 4;
+// therefore cut into chains of at most 512 (split-K across the cluster first, then up to 4 TMEM
+// accumulators per CTA) which are added with ordinary fp32 adds.
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
@@ -145,33 +143,122 @@ struct TcArgs {
     const int* lengths;
     float* q_out;          // LATEST
     float* score;          // LOGITS [n_rows][V]
+    const float* dense_src;  // LOGITS: activation rows [n_rows][K]
     int V, W, B;
+    int bn;                // activation rows per tile: multiple of 16, <= 256 (the UMMA N)
+    int n_stages;          // smem pipeline depth
+    int n_acc;             // TMEM accumulators the CTA's K range is cut into
+    int acc_stride;        // TMEM columns between accumulators (bn rounded up to 32)
+    int tmem_cols;         // power of two >= n_acc * acc_stride
+    long long* dbg;        // optional phase stamps
 };
 
-template <int BN>
-struct TcSmem {
-    static constexpr int kStages = (BN == 128) ? 3 : 4;
-    static constexpr int kABytes = kBM * kBK * 4;   // 16 KB
-    static constexpr int kBBytes = BN * kBK * 4;    // 8 / 16 KB
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers, tmem ptr*/ +
-                                  BN * 8 /*row destinations*/;
-};
+// optional phase stamps (clock64 of one thread per role) for tools/gemm_timing.py: [cta][8]
+//   0 start, 1 setup done, 2 first MMA issued, 3 converters done, 4 accumulators complete,
+//   5 after exchange barrier, 6 after reduce, 7 end
+#define TC_STAMP(slot)                                                                         \
+    do {                                                                                       \
+        if (args.dbg != nullptr && lane == 0 && (warp == 4 || (slot) == 2))                    \
+            args.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); \
+    } while (0)
 
-template <int BN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr int kMaxTcStages = 4;
+constexpr int kMaxBN = 256;
+constexpr int kWBytes = kBM * kBK * 4;          // one 128 x 32 fp32 weight tile: 16 KB
+constexpr int kTcConvThreads = 256;             // warps 4..11
+constexpr int kTcThreadsV2 = 128 + kTcConvThreads;
+
+// ---- cluster / DSMEM helpers -----------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+    float4 v;
+    // not volatile: ordering against the writers comes from the cluster barrier around the reduce
+    asm("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(addr));
+    return v;
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// source row of activation n (nullptr = row absent) and where its 128 outputs of this CTA go
+struct RowIO {
+    const float* src;
+    float* dst;
+};
+__device__ __forceinline__ RowIO row_io(const TcArgs& args, int n, int n_valid, int mat, int f0) {
+    RowIO io{nullptr, nullptr};
+    if (n >= n_valid) return io;
+    if (args.mode == TC_LOGITS) {
+        io.src = args.dense_src + (size_t)n * args.K;
+        io.dst = args.score + (size_t)n * args.V + f0;
+        return io;
+    }
+    int r, j;
+    if (args.mode == TC_LATEST) {
+        r = n;
+        j = args.lengths[r] - 1;
+        if (j < 0) return io;
+    } else {
+        const TileDesc t = args.tiles[n / kTileM];
+        r = t.row;
+        j = t.j0 + (n % kTileM);
+        if (j >= args.lengths[r]) return io;
+    }
+    float* page = args.page_table[(size_t)r * args.W + j / kPage];
+    io.src = page_row_ptr(page, j, args.d, 0);
+    io.dst = (mat == 1) ? args.q_out + (size_t)r * args.d + f0
+                        : page_row_ptr(page, j, args.d, mat == 0 ? 1 : 2) + f0;
+    return io;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cluster split-K 3xTF32 GEMM.  grid = (feature tiles, activation-tile walkers, split), cluster =
+// (1, 1, split): the `split` CTAs of a cluster share one 128 x bn output tile and each contracts a
+// contiguous slice of K; partial tiles are exchanged through distributed shared memory and summed
+// in a fixed order (rank 0, 1, ...), so results do not depend on scheduling.
+//
+//   warp 0      TMA producer: pre-split weight tiles W_hi | W_lo (cp.async.bulk.tensor, 128B swizzle)
+//   warp 1      tcgen05.mma issuer (one lane), commits to the stage / accumulator mbarriers
+//   warp 2      TMEM allocator
+//   warps 4-11  activation path: gather fp32 rows straight from the KV pages (or the dense
+//               attention result), split them into tf32 hi | lo in registers and store them in the
+//               UMMA 128B-swizzled K-major layout -- no staging pass through HBM; afterwards the
+//               same warps drain TMEM (tcgen05.ld) into the partial tile / the destination rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreadsV2, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    TcArgs args) {
-    using SM = TcSmem<BN>;
-    constexpr int kStages = SM::kStages;
     extern __shared__ unsigned char tc_smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TC_STAMP(0);
+    const int bn = args.bn;
+    const int nst = args.n_stages;
+    const int split = gridDim.z;
+    const int krank = blockIdx.z;   // == rank inside the (1,1,split) cluster
+    const int x_bytes = bn * kBK * 4;
+    const int stage_bytes = 2 * kWBytes + 2 * x_bytes;
 
-    // rows this launch really has (device-side for prefill); uniform early exit before any barrier
-    int n_valid = args.n_rows;
-    if (args.mode == TC_PREFILL) n_valid = min(n_valid, *args.n_tiles * kTileM);
-    if ((int)blockIdx.y * BN >= n_valid) return;
+    unsigned char* base = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* ctrl = base + (size_t)nst * stage_bytes;
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(ctrl);
+    uint64_t* full_x = full_w + kMaxTcStages;
+    uint64_t* empty_bar = full_x + kMaxTcStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxTcStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    const float** src_tab = reinterpret_cast<const float**>(ctrl + 256);
+    float** dst_tab = reinterpret_cast<float**>(ctrl + 256 + kMaxBN * 8);
+    float* part = reinterpret_cast<float*>(base);   // [bn][128] partial tile, aliases the stages
 
     // which features does this CTA produce?
     // LATEST: operand rows are [Wk^T; Wq^T; Wv^T] -> mat 0 = K, 1 = q, 2 = V
@@ -184,85 +271,89 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (args.mode == TC_PREFILL && mat == 1) mat = 2;
     }
 
-    unsigned char* base = reinterpret_cast<unsigned char*>(
-        (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* tiles_smem = base;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + kStages * SM::kStageBytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
-    uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
-    float** dst = reinterpret_cast<float**>(base + kStages * SM::kStageBytes + 256);
-
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi);
         prefetch_tmap(&map_a_lo);
-        prefetch_tmap(&map_b_hi);
-        prefetch_tmap(&map_b_lo);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full_w[s], 1);
+            mbar_init(&full_x[s], kTcConvThreads);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, 128);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr_smem, kChunks * BN);
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, (uint32_t)args.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_ptr_smem;
-    const int num_kb = args.K / kBK;
-    const int kb_per_chunk = (num_kb + kChunks - 1) / kChunks;
 
-    // Every CTA owns one 128-feature slab and walks the activation tiles nt = blockIdx.y,
-    // blockIdx.y + gridDim.y, ... (the grid is capped at ~2 CTAs per SM so that a launch whose
-    // device-side row count turns out to be tiny does not pay for thousands of empty CTAs).
-    // Pipeline counters run on across tiles; TMEM is handed back and forth with full/empty barriers.
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int nt = blockIdx.y; nt * BN < n_valid; nt += gridDim.y) {
-                const int n0 = nt * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-                    unsigned char* st = tiles_smem + (size_t)s * SM::kStageBytes;
-                    mbar_expect_tx(&full_bar[s], SM::kStageBytes);
-                    tma_load_2d(st, &map_a_hi, kb * kBK, m0, &full_bar[s]);
-                    tma_load_2d(st + SM::kABytes, &map_a_lo, kb * kBK, m0, &full_bar[s]);
-                    tma_load_2d(st + 2 * SM::kABytes, &map_b_hi, kb * kBK, n0, &full_bar[s]);
-                    tma_load_2d(st + 2 * SM::kABytes + SM::kBBytes, &map_b_lo, kb * kBK, n0, &full_bar[s]);
+    TC_STAMP(1);
+    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
+    griddep_wait();
+    griddep_launch_dependents();
+
+    int n_valid = args.n_rows;
+    if (args.mode == TC_PREFILL) n_valid = min(n_valid, *args.n_tiles * kTileM);
+
+    const int num_kb = args.K / kBK;
+    const int kb_per = num_kb / split;          // host guarantees divisibility
+    const int kb0 = krank * kb_per, kb1 = kb0 + kb_per;
+    const int kb_per_acc = (kb_per + args.n_acc - 1) / args.n_acc;
+
+    uint32_t it = 0;        // pipeline counter (runs on across tiles; identical in every role)
+    uint32_t tile_iter = 0;
+    for (int nt = blockIdx.y; nt * bn < n_valid; nt += gridDim.y, ++tile_iter) {
+        const int n0 = nt * bn;
+        const int n_eff = min(bn, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
+        // ---- row tables of the tile ----
+        if (tid < bn) {
+            const RowIO io = row_io(args, n0 + tid, n_valid, mat, f0);
+            src_tab[tid] = io.src;
+            dst_tab[tid] = io.dst;
+        }
+        __syncthreads();
+
+        if (warp == 0) {
+            // ===================== TMA producer (weights) =====================
+            if (lane == 0) {
+                uint32_t i = it;
+                for (int kb = kb0; kb < kb1; ++kb, ++i) {
+                    const int s = i % nst;
+                    mbar_wait(&empty_bar[s], ((i / nst) & 1) ^ 1);
+                    unsigned char* st = base + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_w[s], 2 * kWBytes);
+                    tma_load_2d(st, &map_a_hi, kb * kBK, m0, &full_w[s]);
+                    tma_load_2d(st + kWBytes, &map_a_lo, kb * kBK, m0, &full_w[s]);
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
-            uint32_t it = 0, tile_iter = 0;
-            for (int nt = blockIdx.y; nt * BN < n_valid; nt += gridDim.y, ++tile_iter) {
-                if (tile_iter > 0) {   // epilogue must have drained the accumulators of the last tile
-                    mbar_wait(tmem_empty_bar, (tile_iter - 1) & 1);
+            __syncwarp();
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            if (lane == 0) {
+                const uint32_t idesc = make_idesc_tf32(kBM, n_eff);
+                uint32_t i = it;
+                for (int kb = kb0; kb < kb1; ++kb, ++i) {
+                    const int s = i % nst;
+                    const uint32_t ph = (i / nst) & 1;
+                    mbar_wait(&full_w[s], ph);
+                    mbar_wait(&full_x[s], ph);
                     tc_fence_after();
-                }
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(&full_bar[s], (it / kStages) & 1);
-                    tc_fence_after();
-                    unsigned char* st = tiles_smem + (size_t)s * SM::kStageBytes;
+                    unsigned char* st = base + (size_t)s * stage_bytes;
                     const uint64_t a_hi = make_kmajor_sw128_desc(st);
-                    const uint64_t a_lo = make_kmajor_sw128_desc(st + SM::kABytes);
-                    const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * SM::kABytes);
-                    const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * SM::kABytes + SM::kBBytes);
+                    const uint64_t a_lo = make_kmajor_sw128_desc(st + kWBytes);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kWBytes);
+                    const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * kWBytes + x_bytes);
+                    const int rel = kb - kb0;
+                    const uint32_t acc = tmem_acc + (uint32_t)((rel / kb_per_acc) * args.acc_stride);
+                    const bool first_kb = (rel % kb_per_acc) == 0;
+                    if (kb == kb0) TC_STAMP(2);
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint64_t koff = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 B per k-step
-                        const uint32_t acc = tmem_acc + (uint32_t)((kb / kb_per_chunk) * BN);
-                        umma_tf32(acc, a_lo + koff, b_hi + koff, idesc, ((kb % kb_per_chunk) | k) != 0);
+                        umma_tf32(acc, a_lo + koff, b_hi + koff, idesc, (first_kb && k == 0) ? 0u : 1u);
                         umma_tf32(acc, a_hi + koff, b_lo + koff, idesc, 1);
                         umma_tf32(acc, a_hi + koff, b_hi + koff, idesc, 1);
                     }
@@ -270,78 +361,128 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 }
                 umma_commit(tmem_full_bar);       // accumulators of this tile complete
             }
-        }
-    } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int et = threadIdx.x - 128;  // 0..127
-        const int ew = warp - 4;           // TMEM lane quadrant of this warp
-        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
-        const int n_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
-        uint32_t tile_iter = 0;
-        for (int nt = blockIdx.y; nt * BN < n_valid; nt += gridDim.y, ++tile_iter) {
-            const int n0 = nt * BN;
-            named_bar_sync(1, 128);   // previous tile's stores no longer read dst[]
-            // destination of activation row n0 + i (base pointer for this CTA's feature range)
-            for (int i = et; i < BN; i += 128) {
-                const int n = n0 + i;
-                float* p = nullptr;
-                if (n < n_valid) {
-                    if (args.mode == TC_LOGITS) {
-                        p = args.score + (size_t)n * args.V + f0;
-                    } else {
-                        int r, j;
-                        bool ok;
-                        if (args.mode == TC_LATEST) {
-                            r = n;
-                            const int L = args.lengths[r];
-                            j = L - 1;
-                            ok = L > 0;
-                        } else {
-                            const TileDesc t = args.tiles[n / kTileM];
-                            r = t.row;
-                            j = t.j0 + (n % kTileM);
-                            ok = j < args.lengths[r];
-                        }
-                        if (ok) {
-                            if (mat == 1) {
-                                p = args.q_out + (size_t)r * args.d + f0;
-                            } else {
-                                float* page = args.page_table[(size_t)r * args.W + j / kPage];
-                                p = page_row_ptr(page, j, args.d, mat == 0 ? 1 : 2) + f0;
-                            }
-                        }
+            __syncwarp();
+        } else if (warp >= 4) {
+            // ===================== activation gather + tf32 split =====================
+            const int c = tid - 128;            // 0..255
+            const int chunk = c & 7;            // 16-byte chunk of the 128-byte k-slice
+            const int rbase = c >> 3;           // rows rbase, rbase + 32, ...
+            const float4* rp[kMaxBN / 32];
+#pragma unroll
+            for (int i = 0; i < kMaxBN / 32; ++i) {
+                const int r = rbase + 32 * i;
+                const float* p = (r < n_eff) ? src_tab[r] : nullptr;
+                rp[i] = p ? reinterpret_cast<const float4*>(p) + chunk : nullptr;
+            }
+            // two register sets (even / odd k-blocks): the loads of k-block kb+2 are in flight while
+            // k-block kb+1 is converted, so global latency is off the per-stage critical path
+            float4 ra[kMaxBN / 32], rb[kMaxBN / 32];
+            auto load_set = [&](float4 (&dst)[kMaxBN / 32], int kb) {
+#pragma unroll
+                for (int i = 0; i < kMaxBN / 32; ++i)
+                    dst[i] = rp[i] ? ldg_stream(rp[i] + kb * (kBK / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            auto store_set = [&](const float4 (&src)[kMaxBN / 32], uint32_t i2) {
+                const int s = i2 % nst;
+                mbar_wait(&empty_bar[s], ((i2 / nst) & 1) ^ 1);
+                unsigned char* xh = base + (size_t)s * stage_bytes + 2 * kWBytes;
+                unsigned char* xl = xh + x_bytes;
+#pragma unroll
+                for (int i = 0; i < kMaxBN / 32; ++i) {
+                    const int r = rbase + 32 * i;
+                    if (r < n_eff) {
+                        const float4 v = src[i];
+                        const float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z),
+                                                     to_tf32_rna(v.w));
+                        const float4 l = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y),
+                                                     to_tf32_rna(v.z - h.z), to_tf32_rna(v.w - h.w));
+                        const int off = r * 128 + ((chunk ^ (r & 7)) << 4);   // 128B swizzle
+                        *reinterpret_cast<float4*>(xh + off) = h;
+                        *reinterpret_cast<float4*>(xl + off) = l;
                     }
                 }
-                dst[i] = p;
+                fence_proxy_async_smem();
+                mbar_arrive(&full_x[s]);
+            };
+            load_set(ra, kb0);
+            if (kb0 + 1 < kb1) load_set(rb, kb0 + 1);
+            uint32_t i2 = it;
+            for (int kb = kb0; kb < kb1; kb += 2, i2 += 2) {
+                store_set(ra, i2);
+                if (kb + 2 < kb1) load_set(ra, kb + 2);
+                if (kb + 1 < kb1) {
+                    store_set(rb, i2 + 1);
+                    if (kb + 3 < kb1) load_set(rb, kb + 3);
+                }
             }
-            named_bar_sync(1, 128);
+            TC_STAMP(3);
+
+            // ===================== epilogue: TMEM -> partial tile / destination rows =====================
             mbar_wait(tmem_full_bar, tile_iter & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            TC_STAMP(4);
+            const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+            const int half = (warp - 4) >> 2;        // two warps per quadrant split the columns
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            for (int c0 = half * 32; c0 < n_eff; c0 += 64) {
                 float v[32];
                 tmem_ld32(tmem_acc + lane_base + (uint32_t)c0, v);
-                for (int ch = 1; ch < n_chunks; ++ch) {
+                for (int a = 1; a < args.n_acc; ++a) {
                     float u[32];
-                    tmem_ld32(tmem_acc + lane_base + (uint32_t)(ch * BN + c0), u);
+                    tmem_ld32(tmem_acc + lane_base + (uint32_t)(a * args.acc_stride + c0), u);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += u[j];
                 }
+                if (split == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float* p = dst[c0 + j];
-                    if (p != nullptr) p[ew * 32 + lane] = v[j];   // 32 lanes -> 128 contiguous bytes
+                    for (int j = 0; j < 32; ++j) {
+                        float* p = (c0 + j < n_eff) ? dst_tab[c0 + j] : nullptr;
+                        if (p != nullptr) p[q * 32 + lane] = v[j];   // 32 lanes -> 128 contiguous bytes
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < n_eff) part[(size_t)(c0 + j) * kBM + q * 32 + lane] = v[j];
                 }
             }
             tc_fence_before();
-            mbar_arrive(tmem_empty_bar);   // accumulators may be overwritten by the next tile
         }
+        // ---- split-K exchange: rank z sums rows z, z + split, ... of all partial tiles ----
+        cluster_sync_all();
+        TC_STAMP(5);
+        if (split > 1) {
+            const int f4 = tid & 31;
+            uint32_t raddr[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) raddr[r] = dsmem_addr(part + f4 * 4, (uint32_t)(r < split ? r : 0));
+            for (int n = krank + split * (tid >> 5); n < n_eff; n += split * (kTcThreadsV2 / 32)) {
+                float* p = dst_tab[n];
+                if (p == nullptr) continue;
+                float4 t[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < split) t[r] = ld_dsmem_f4(raddr[r] + (uint32_t)n * (kBM * 4));
+                float4 sum = t[0];
+#pragma unroll
+                for (int r = 1; r < 8; ++r)
+                    if (r < split) { sum.x += t[r].x; sum.y += t[r].y; sum.z += t[r].z; sum.w += t[r].w; }
+                reinterpret_cast<float4*>(p)[f4] = sum;
+            }
+        }
+        TC_STAMP(6);
+        // the partial tile aliases the pipeline stages: order these generic-proxy accesses before
+        // the next tile's TMA (async proxy) writes
+        asm volatile("fence.proxy.async;" ::: "memory");
+        cluster_sync_all();   // partial tiles and row tables may be reused
+        tc_fence_after();
+        it += (uint32_t)kb_per;
     }
     tc_fence_before();
     __syncthreads();
+    TC_STAMP(7);
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_acc, kChunks * BN);
+        tmem_dealloc(tmem_acc, (uint32_t)args.tmem_cols);
     }
 }
 
@@ -376,40 +517,6 @@ __global__ void split_matrix_kernel(const float4* __restrict__ x, float4* __rest
         hi[i] = h;
         lo[i] = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y), to_tf32_rna(v.z - h.z),
                             to_tf32_rna(v.w - h.w));
-    }
-}
-
-// gather the activation rows of a launch and split them: one warp per row
-__global__ void __launch_bounds__(256)
-gather_split_rows_kernel(TcArgs args, const float* __restrict__ dense_src, float* __restrict__ hi,
-                         float* __restrict__ lo) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int n_valid = args.n_rows;
-    if (args.mode == TC_PREFILL) n_valid = min(n_valid, *args.n_tiles * kTileM);
-    const int d4 = args.K >> 2;
-    for (int n = blockIdx.x * 8 + warp; n < n_valid; n += gridDim.x * 8) {
-        const float* src = nullptr;
-        if (args.mode == TC_LOGITS) {
-            src = dense_src + (size_t)n * args.K;
-        } else if (args.mode == TC_LATEST) {
-            const int L = args.lengths[n];
-            if (L > 0)
-                src = page_row_ptr(args.page_table[(size_t)n * args.W + (L - 1) / kPage], L - 1, args.d, 0);
-        } else {
-            const TileDesc t = args.tiles[n / kTileM];
-            const int j = t.j0 + (n % kTileM);
-            if (j < args.lengths[t.row])
-                src = page_row_ptr(args.page_table[(size_t)t.row * args.W + j / kPage], j, args.d, 0);
-        }
-        float4* h4 = reinterpret_cast<float4*>(hi + (size_t)n * args.K);
-        float4* l4 = reinterpret_cast<float4*>(lo + (size_t)n * args.K);
-        for (int c = lane; c < d4; c += 32) {
-            float4 v = src ? reinterpret_cast<const float4*>(src)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
-            h4[c] = h;
-            l4[c] = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y), to_tf32_rna(v.z - h.z),
-                                to_tf32_rna(v.w - h.w));
-        }
     }
 }
 
@@ -530,79 +637,85 @@ int get_operand(mli_ctx* ctx, const float* p0, const float* p1, const float* p2,
     return 0;
 }
 
-// activation staging (hi | lo) with cached tensor maps per (pointer, rows, K, BN)
-struct StageMaps {
-    float* base;
-    size_t rows;
-    int K, bn;
-    CUtensorMap hi, lo;
-};
-std::vector<StageMaps> g_stage_maps;
+bool shapes_ok(int K, int feat_per_mat) { return K % 128 == 0 && feat_per_mat % kBM == 0 && K >= 128; }
 
-int get_staging(mli_ctx* ctx, size_t rows, int K, int bn, float** hi, float** lo, const CUtensorMap** mh,
-                const CUtensorMap** ml) {
-    void* p = nullptr;
-    int rc = ws_get(ctx, WS_GEMM_A, sizeof(float) * 2 * rows * K, &p);
-    if (rc) return rc;
-    float* base = reinterpret_cast<float*>(p);
-    *hi = base;
-    *lo = base + rows * K;
-    std::lock_guard<std::mutex> lk(g_tc_mu);
-    for (auto& m : g_stage_maps)
-        if (m.base == base && m.rows == rows && m.K == K && m.bn == bn) {
-            *mh = &m.hi;
-            *ml = &m.lo;
-            return 0;
-        }
-    StageMaps m{};
-    m.base = base;
-    m.rows = rows;
-    m.K = K;
-    m.bn = bn;
-    if ((rc = make_map(&m.hi, *hi, rows, K, bn))) return rc;
-    if ((rc = make_map(&m.lo, *lo, rows, K, bn))) return rc;
-    if (g_stage_maps.size() > 64) g_stage_maps.erase(g_stage_maps.begin());
-    g_stage_maps.push_back(m);
-    *mh = &g_stage_maps.back().hi;
-    *ml = &g_stage_maps.back().lo;
-    return 0;
+size_t tc_smem_bytes(int n_stages, int bn) {
+    return (size_t)n_stages * (2 * kWBytes + 2 * (size_t)bn * kBK * 4) + 1024 /*align*/ + 256 /*barriers*/ +
+           2 * kMaxBN * 8 /*row tables*/;
 }
 
-bool shapes_ok(int K, int feat_per_mat) { return K % kBK == 0 && feat_per_mat % kBM == 0 && K >= kBK; }
+// Tile / split selection.  Per-CTA operand traffic is what bounds these GEMMs at decode sizes
+// (one SM ingests ~60-100 GB/s), so the activation tile is made as wide as the UMMA allows
+// (weights are then read once per 256 rows) and K is split across a cluster until the launch
+// covers the GPU in a single wave.
+int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int expect_rows) {
+    const long long rows = args.n_rows;
+    if (rows <= 0) return 0;
+    // expect_rows: rows the launch will typically see (prefill: device-side count, usually small)
+    long long plan_rows = expect_rows > 0 ? std::min<long long>(rows, expect_rows) : rows;
+    const int n_tiles_plan = (int)((plan_rows + kMaxBN - 1) / kMaxBN);
+    long long per_tile = (plan_rows + n_tiles_plan - 1) / n_tiles_plan;
+    int bn = (int)((per_tile + 15) / 16 * 16);
+    if (bn > kMaxBN) bn = kMaxBN;
+    if (rows > plan_rows) bn = kMaxBN;            // the device count may exceed the plan: full-width tiles
+    const int n_tiles_all = (int)((rows + bn - 1) / bn);
+    const int num_kb = args.K / kBK;
+    int split = 1;
+    for (int s = 8; s >= 2; s >>= 1) {
+        if (num_kb % s == 0 && num_kb / s >= 2 && (long long)m_tiles * n_tiles_plan * s <= ctx->num_sms) {
+            split = s;
+            break;
+        }
+    }
+    int ny = n_tiles_all;
+    const int cap = std::max(1, ctx->num_sms / (m_tiles * split));
+    if (ny > cap) ny = std::max(cap, std::min(n_tiles_plan, n_tiles_all));
+    args.bn = bn;
+    args.acc_stride = (bn + 31) / 32 * 32;
+    const int k_per_cta = args.K / split;
+    int n_acc = (k_per_cta + 511) / 512;           // fp32 chains of at most 512 (see kChunks note above)
+    if (n_acc > 512 / args.acc_stride) n_acc = 512 / args.acc_stride;
+    if (n_acc < 1) n_acc = 1;
+    if (n_acc > num_kb / split) n_acc = num_kb / split;
+    args.n_acc = n_acc;
+    int cols = 32;
+    while (cols < n_acc * args.acc_stride) cols <<= 1;
+    args.tmem_cols = cols;
+    int nst = (int)((200 * 1024) / (2 * kWBytes + 2 * (size_t)bn * kBK * 4));
+    if (nst > kMaxTcStages) nst = kMaxTcStages;
+    if (nst < 2) nst = 2;
+    args.n_stages = nst;
+    args.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
+    const size_t smem = tc_smem_bytes(nst, bn);
 
-template <int BN>
-int launch_tc(mli_ctx* ctx, const OperandEntry* w, const CUtensorMap* mbh, const CUtensorMap* mbl, dim3 grid,
-              const TcArgs& args) {
-    auto kern = gemm_tf32x3_kernel<BN>;
     static bool configured = false;
     if (!configured) {
-        MLI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
+        MLI_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc_smem_bytes(2, kMaxBN)));
         configured = true;
     }
-    kern<<<grid, kTcThreads, TcSmem<BN>::kTotal, ctx->stream>>>(w->map_hi, w->map_lo, *mbh, *mbl, args);
-    MLI_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);
+    cfg.blockDim = dim3(kTcThreadsV2);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 1;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = (unsigned)split;
+    ++na;
+    if (ctx->use_pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = (unsigned)na;
+    MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel, w->map_hi, w->map_lo, args));
+    count_launch();
     return 0;
-}
-
-int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, const float* dense_src, int m_tiles) {
-    const size_t rows = (size_t)args.n_rows;
-    // BN = 64 when 128-wide tiles would leave most SMs idle
-    const bool bn64 = (long long)m_tiles * ((rows + 127) / 128) < ctx->num_sms;
-    const int bn = bn64 ? 64 : 128;
-    float *hi, *lo;
-    const CUtensorMap *mh, *ml;
-    int rc = get_staging(ctx, rows, args.K, bn, &hi, &lo, &mh, &ml);
-    if (rc) return rc;
-    int ggrid = (int)((rows + 7) / 8);
-    if (ggrid > ctx->num_sms * 8) ggrid = ctx->num_sms * 8;
-    gather_split_rows_kernel<<<ggrid, 256, 0, ctx->stream>>>(args, dense_src, hi, lo);
-    MLI_LAUNCH_CHECK();
-    // cap the grid at ~2 CTAs per SM; CTAs walk the remaining activation tiles themselves
-    unsigned ny = (unsigned)((rows + bn - 1) / bn);
-    const unsigned cap = (unsigned)((2 * ctx->num_sms + m_tiles - 1) / m_tiles);
-    if (ny > cap) ny = cap;
-    dim3 grid(m_tiles, ny);
-    return bn64 ? launch_tc<64>(ctx, w, mh, ml, grid, args) : launch_tc<128>(ctx, w, mh, ml, grid, args);
 }
 
 }  // namespace
@@ -663,14 +776,13 @@ int launch_qkv_latest_paged_tc(mli_ctx* ctx, float* const* page_table, const int
     TcArgs a{};
     a.mode = TC_LATEST; a.K = d; a.d = d; a.n_rows = B; a.page_table = page_table; a.lengths = lengths;
     a.q_out = q_output; a.W = S / kPage; a.B = B;
-    return run_gemm(ctx, w, a, nullptr, 3 * d / kBM);
+    return run_gemm(ctx, w, a, 3 * d / kBM, 0);
 }
 
 int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const TileDesc* tiles,
                                const int* n_tiles, int max_tiles, const int* lengths,
                                const float* wk, const float* wv, int S, int d) {
-    // staging holds hi|lo copies of every row the launch could cover; past 4 GiB use the SIMT path
-    if (!shapes_ok(d, d) || max_tiles <= 0 || (size_t)max_tiles * kTileM * d * 8 > (size_t(4) << 30))
+    if (!shapes_ok(d, d) || max_tiles <= 0)
         return launch_prefill_kv_paged_simt(ctx, page_table, tiles, n_tiles, max_tiles, lengths, wk, wv, S, d);
     OperandEntry* w = nullptr;
     int rc = get_operand(ctx, wk, wv, nullptr, 2 * d, d, &w);
@@ -678,7 +790,9 @@ int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const Til
     TcArgs a{};
     a.mode = TC_PREFILL; a.K = d; a.d = d; a.n_rows = max_tiles * kTileM; a.n_tiles = n_tiles; a.tiles = tiles;
     a.page_table = page_table; a.lengths = lengths; a.W = S / kPage;
-    return run_gemm(ctx, w, a, nullptr, 2 * d / kBM);
+    // the tile count is only known on the device; admissions per engine step are few, so plan the
+    // split for one activation tile and let the clusters walk the rest when there is more
+    return run_gemm(ctx, w, a, 2 * d / kBM, kMaxBN);
 }
 
 int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V, int d) {
@@ -688,7 +802,8 @@ int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* s
     if (rc) return rc;
     TcArgs a{};
     a.mode = TC_LOGITS; a.K = d; a.d = d; a.n_rows = B; a.score = score; a.V = V; a.B = B;
-    return run_gemm(ctx, w, a, attn, V / kBM);
+    a.dense_src = attn;
+    return run_gemm(ctx, w, a, V / kBM, 0);
 }
 
 }  // namespace mli

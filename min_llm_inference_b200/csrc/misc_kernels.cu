@@ -21,6 +21,8 @@ __global__ void build_new_row_tiles_kernel(const int* __restrict__ new_idx,
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
+    griddep_wait();
+    griddep_launch_dependents();
     const int n_new = n_new_dev ? *n_new_dev : n_new_host;
     if (tid == 0) carry_s = 0;
     __syncthreads();
@@ -66,10 +68,8 @@ __global__ void build_new_row_tiles_kernel(const int* __restrict__ new_idx,
 
 int launch_build_new_row_tiles(mli_ctx* ctx, const int* new_idx, const int* lengths, int n_new_host,
                                const int* n_new_dev, TileDesc* tiles, int* n_tiles, int max_tiles) {
-    build_new_row_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(new_idx, lengths, n_new_host, n_new_dev,
-                                                            tiles, n_tiles, max_tiles);
-    MLI_LAUNCH_CHECK();
-    return 0;
+    return launch_kernel(ctx, build_new_row_tiles_kernel, dim3(1), dim3(1024), 0, new_idx, lengths,
+                         n_new_host, n_new_dev, tiles, n_tiles, max_tiles);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -84,6 +84,8 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
                            const int* __restrict__ lengths, int S, int d) {
     const int W = S / kPage, d4 = d >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    griddep_wait();
+    griddep_launch_dependents();
     const int nt = *n_tiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const TileDesc td = tiles[t];
@@ -113,11 +115,8 @@ int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos,
     int grid = ctx->num_sms * 4;
     if (grid > max_tiles) grid = max_tiles;
     if (grid < 1) grid = 1;
-    paged_encoder_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(emb, pos, inp, row_req, req_tok,
-                                                              page_table, tiles, n_tiles, lengths, S,
-                                                              d);
-    MLI_LAUNCH_CHECK();
-    return 0;
+    return launch_kernel(ctx, paged_encoder_tiles_kernel, dim3(grid), dim3(256), 0, emb, pos, inp, row_req,
+                         req_tok, page_table, tiles, n_tiles, lengths, S, d);
 }
 
 // dense encoder (src/kernels/encoder.cu:56-92); element-wise so any emb_dim works
@@ -162,6 +161,8 @@ decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result
                const float* __restrict__ emb, int V, int S, int d, int n_dec, int i_dec) {
     const int r = blockIdx.x;
     const int tid = threadIdx.x;
+    griddep_wait();
+    griddep_launch_dependents();
     const int L = lengths[r];
     if (L == 0) {
         if (tid == 0) decoder_result[(size_t)r * n_dec + i_dec] = MLI_EMPTY_ROW_TOKEN_ID;
@@ -215,19 +216,15 @@ decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result
 int launch_paged_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
                          float* const* page_table, const float* pos, const float* emb, int B, int V,
                          int S, int d, int n_dec, int i_dec) {
-    decoder_kernel<true><<<B, 256, 0, ctx->stream>>>(score, decoder_result, lengths, page_table,
-                                                     nullptr, pos, emb, V, S, d, n_dec, i_dec);
-    MLI_LAUNCH_CHECK();
-    return 0;
+    return launch_kernel(ctx, decoder_kernel<true>, dim3(B), dim3(256), 0, score, decoder_result, lengths,
+                         page_table, static_cast<float*>(nullptr), pos, emb, V, S, d, n_dec, i_dec);
 }
 
 int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
                          float* inp_embedding, const float* pos, const float* emb, int B, int V, int S,
                          int d) {
-    decoder_kernel<false><<<B, 256, 0, ctx->stream>>>(score, decoder_result, lengths, nullptr,
-                                                      inp_embedding, pos, emb, V, S, d, 1, 0);
-    MLI_LAUNCH_CHECK();
-    return 0;
+    return launch_kernel(ctx, decoder_kernel<false>, dim3(B), dim3(256), 0, score, decoder_result, lengths,
+                         static_cast<float* const*>(nullptr), inp_embedding, pos, emb, V, S, d, 1, 0);
 }
 
 }  // namespace mli
