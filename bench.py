@@ -91,6 +91,24 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+class StdoutToStderr:
+    """the reference's ThroughputCounter printf()s to fd 1; keep stdout to the one JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        import ctypes
+        try:
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ---------------------------------------------------------------------------------------------
 def reference_arm(args, rank, world):
     """the reference's own CPU implementation of the path (oracle/_ref), bounded sample"""
@@ -113,11 +131,12 @@ def reference_arm(args, rank, world):
         kind, cores = "reference", 1
         for i in range(args.warmup + args.steps):
             gen, steps, sec = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
-            H.check_ref(ref.ref_run_host_engine(sample_rows, wl["S"], wl["d"], wl["V"], H.p(w["emb"]),
-                                                H.p(w["pos"]), H.p(w["wk"]), H.p(w["wq"]), H.p(w["wv"]),
-                                                sample_rows, H.p(offs_s), H.p(toks_s), sample_iters,
-                                                C.byref(gen), C.byref(steps), C.byref(sec), None, None,
-                                                None, None))
+            with StdoutToStderr():
+                H.check_ref(ref.ref_run_host_engine(sample_rows, wl["S"], wl["d"], wl["V"], H.p(w["emb"]),
+                                                    H.p(w["pos"]), H.p(w["wk"]), H.p(w["wq"]), H.p(w["wv"]),
+                                                    sample_rows, H.p(offs_s), H.p(toks_s), sample_iters,
+                                                    C.byref(gen), C.byref(steps), C.byref(sec), None, None,
+                                                    None, None))
             if i >= args.warmup:
                 times.append(sec.value)
                 gens.append(gen.value)
@@ -411,7 +430,8 @@ def main():
             except Exception as e:  # never lose the headline line to an extra
                 line["roofline_long_context"] = {"error": str(e)[:200]}
             try:
-                line["reference_cuda"] = reference_cuda_leg(w, offs, toks)
+                with StdoutToStderr():
+                    line["reference_cuda"] = reference_cuda_leg(w, offs, toks)
             except Exception as e:
                 line["reference_cuda"] = {"error": str(e)[:200]}
             try:

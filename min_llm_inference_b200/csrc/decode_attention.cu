@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace mli {
@@ -89,12 +90,22 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-// FUSED = true: the item list is derived inside the kernel (every CTA scans the lengths into a
-// shared-memory prefix; B <= kMaxFusedRows) and split partials are merged by whichever CTA finishes
-// a row's last chunk (per-row arrival counter in global memory, self-resetting) -- ONE launch per
-// decode step.  FUSED = false: item list from attn_prep_kernel, merge by attn_combine_kernel (used
-// when the [B,S] probabilities are requested or B is too large for the shared-memory prefix).
+// FUSED = true (the production path, ONE launch per decode step): every CTA scans the lengths into
+// a shared-memory prefix over POSITIONS and takes an equal, contiguous slice of the flattened
+// position space (stream-K style: bytes per CTA are balanced exactly, whatever the mix of row
+// lengths).  A slice may start or end inside a row; such partial rows (at most two per CTA: its
+// head and its tail) are merged by whichever CTA finishes the row's last segment (per-row arrival
+// counter in global memory, self-resetting).  B <= kMaxFusedRows.
+// FUSED = false: (row, chunk) items from attn_prep_kernel, merge by attn_combine_kernel -- used when
+// the [B,S] probabilities are requested or B is too large for the shared-memory prefix.
 constexpr int kMaxFusedRows = 4096;
+
+struct AttnSeg {
+    int r;        // batch row
+    int p0, p1;   // positions [p0, p1) of the row
+    int nseg;     // segments the row is cut into (1 = this one produces the final output)
+    int pidx;     // partial slot of this segment
+};
 
 template <int NC, int G, bool FUSED>
 __global__ void __launch_bounds__(kAttnThreads)
@@ -103,7 +114,11 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         const int* __restrict__ item_row, const int* __restrict__ item_chunk,
                         float* __restrict__ out, float* __restrict__ part_acc,
                         float* __restrict__ part_ml, float* __restrict__ scores_out,
-                        int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage) {
+                        int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage,
+                        long long* __restrict__ dbg) {
+    // optional phase stamps (tools/attn_timing.py): [cta][8] clock64 of consumer thread 0
+#define ATTN_STAMP(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+    ATTN_STAMP(0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = S / kPage;
     const int d4 = d >> 2;
@@ -114,7 +129,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     uint64_t* empty_bar = full_bar + kMaxStages;
     float* red = reinterpret_cast<float*>(empty_bar + kMaxStages);  // [2][kConsumerWarps][G]
     int* scan_tmp = reinterpret_cast<int*>(red + 2 * kConsumerWarps * G);   // [16]: warp totals, carry, flag
-    int* row_first_s = scan_tmp + 16;                                        // FUSED: [B + 1]
+    int* pos_first = scan_tmp + 16;                                          // FUSED: [B + 1]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -130,16 +145,18 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     __syncthreads();
     griddep_wait();
     griddep_launch_dependents();
+    ATTN_STAMP(1);
 
-    int n_items;
+    int n_items = 0;      // legacy: number of (row, chunk) items
+    int quantum = 0;      // fused: positions per CTA
+    int g0 = 0, g1 = 0;   // fused: this CTA's slice of the flattened position space
     if constexpr (FUSED) {
-        // exclusive prefix of chunk counts over the rows, kAttnThreads rows at a time
+        // exclusive prefix of the lengths, kAttnThreads rows at a time
         if (tid == 0) scan_tmp[12] = 0;
         __syncthreads();
         for (int base = 0; base < B; base += kAttnThreads) {
             const int r = base + tid;
-            const int L = (r < B) ? lengths[r] : 0;
-            const int n = (L + chunk_pos - 1) / chunk_pos;
+            const int n = (r < B) ? lengths[r] : 0;
             int v = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -150,50 +167,74 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             __syncthreads();
             int before = scan_tmp[12];
             for (int w = 0; w < warp; ++w) before += scan_tmp[w];
-            if (r < B) row_first_s[r] = before + v - n;
+            if (r < B) pos_first[r] = before + v - n;
             __syncthreads();
             if (tid == kAttnThreads - 1) scan_tmp[12] = before + v;
             __syncthreads();
         }
-        n_items = scan_tmp[12];
-        if (tid == 0) row_first_s[B] = n_items;
+        const int P = scan_tmp[12];
+        if (tid == 0) pos_first[B] = P;
         __syncthreads();
+        quantum = (P + (int)gridDim.x - 1) / (int)gridDim.x;
+        quantum = max(G, (quantum + G - 1) / G * G);
+        g0 = min(P, (int)blockIdx.x * quantum);
+        g1 = min(P, g0 + quantum);
     } else {
         n_items = row_first_g[B];
     }
-    // item -> (row, chunk)
-    auto locate = [&](int item, int& r, int& c) {
+
+    // work iterator, identical in the producer and the consumers.  `cur` is a global position
+    // (fused) or an item index (legacy).
+    auto next_seg = [&](int& cur, AttnSeg& sg) -> bool {
         if constexpr (FUSED) {
-            int lo = 0, hi = B;
+            if (cur >= g1) return false;
+            int lo = 0, hi = B;   // largest r with pos_first[r] <= cur (empty rows share a start: skipped)
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (row_first_s[mid] <= item) lo = mid; else hi = mid;
+                if (pos_first[mid] <= cur) lo = mid; else hi = mid;
             }
-            r = lo;
-            c = item - row_first_s[lo];
+            const int start = pos_first[lo], L = pos_first[lo + 1] - start;
+            sg.r = lo;
+            sg.p0 = cur - start;
+            sg.p1 = min(g1 - start, L);
+            sg.nseg = (start + L - 1) / quantum - start / quantum + 1;
+            sg.pidx = 2 * (int)blockIdx.x + (cur == g0 ? 0 : 1);
+            cur = start + sg.p1;
+            return true;
         } else {
-            r = item_row[item];
-            c = item_chunk[item];
+            if (cur >= n_items) return false;
+            const int r = item_row[cur], c = item_chunk[cur];
+            const int L = lengths[r];
+            sg.r = r;
+            sg.p0 = c * chunk_pos;
+            sg.p1 = min(L, sg.p0 + chunk_pos);
+            sg.nseg = (L + chunk_pos - 1) / chunk_pos;
+            sg.pidx = cur;
+            cur += gridDim.x;
+            return true;
         }
     };
+    int cur = FUSED ? g0 : (int)blockIdx.x;
+    AttnSeg sg;
+    ATTN_STAMP(2);
 
     if (warp == kConsumerWarps) {
         // ===================== producer warp =====================
-        uint32_t it = 0;  // running stage counter across items
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int r, c;
-            locate(item, r, c);
-            const int L = lengths[r];
-            const int p0 = c * chunk_pos;
-            const int p1 = min(L, p0 + chunk_pos);
-            // page pointers of this chunk: lane i holds page (c*CH + i)
-            const int npages = (p1 - p0 + kPage - 1) / kPage;
+        uint32_t it = 0;  // running stage counter across segments
+        while (next_seg(cur, sg)) {
+            const int r = sg.r, p1 = sg.p1;
+            // page pointers are fetched 32 pages at a time: lane i holds page (pgb + i)
+            int pgb = -(1 << 30);
             const float* my_page = nullptr;
-            if (lane < npages) my_page = page_table[(size_t)r * W + (size_t)c * chunk_pages + lane];
-            for (int pos = p0; pos < p1; pos += G, ++it) {
+            for (int pos = sg.p0; pos < p1; pos += G, ++it) {
                 const int stage = it % nstage;
                 const uint32_t parity = (it / nstage) & 1u;
                 const int nvalid = min(G, p1 - pos);
+                if (pos / kPage < pgb || (pos + nvalid - 1) / kPage >= pgb + 32) {
+                    pgb = pos / kPage;
+                    const int pg = pgb + lane;
+                    my_page = (pg * kPage < p1) ? page_table[(size_t)r * W + pg] : nullptr;
+                }
                 if (lane == 0) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);
                     mbar_expect_tx(&full_bar[stage], (uint32_t)nvalid * row_floats * 4u);
@@ -201,7 +242,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                 __syncwarp();
                 // lane g copies position pos+g (K|V rows are contiguous: 8*d bytes)
                 const int j = pos + (lane < G ? lane : 0);
-                const int pg = (j - p0) / kPage;
+                const int pg = min(j / kPage - pgb, 31);
                 const float* page = reinterpret_cast<const float*>(
                     __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_page), pg));
                 if (lane < nvalid) {
@@ -219,19 +260,16 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     if constexpr (FUSED) {
         // empty rows produce zeros (the reference stores result = 0, paged_attention.cu:289,:323)
         for (int r = blockIdx.x; r < B; r += gridDim.x) {
-            if (lengths[r] != 0) continue;
+            if (pos_first[r + 1] != pos_first[r]) continue;
             for (int col = tid; col < d4; col += kConsumerThreads)
                 reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int r, c;
-        locate(item, r, c);
-        const int L = lengths[r];
-        const int p0 = c * chunk_pos;
-        const int p1 = min(L, p0 + chunk_pos);
-        const int nchunks = (L + chunk_pos - 1) / chunk_pos;
+    int pend_r[2], pend_nseg[2], n_pend = 0;   // partial rows of this slice (head, tail)
+    ATTN_STAMP(3);
+    while (next_seg(cur, sg)) {
+        const int r = sg.r, p0 = sg.p0, p1 = sg.p1;
 
         float4 qv[NC];
         float4 acc[NC];
@@ -251,6 +289,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             const float* sbase = ring + (size_t)stage * stage_floats;
             float* red_buf = red + (size_t)(it & 1u) * kConsumerWarps * G;
             mbar_wait(&full_bar[stage], parity);
+            if (it == 0) ATTN_STAMP(4);
 
             // ---- phase A: partial q.K over this thread's columns, warp reduce ----
 #pragma unroll
@@ -324,11 +363,14 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
         }
 
-        // ---- item epilogue ----
-        if (nchunks == 1) {
+        // ---- segment epilogue ----
+        ATTN_STAMP(5);
+        const int nseg = sg.nseg;
+        const size_t pidx = (size_t)sg.pidx;
+        if (nseg == 1) {
             if (!FUSED && tid == 0) {
-                part_ml[2 * (size_t)item] = m_run;
-                part_ml[2 * (size_t)item + 1] = l_run;
+                part_ml[2 * pidx] = m_run;
+                part_ml[2 * pidx + 1] = l_run;
             }
             const float norm = 1.f / l_run;
 #pragma unroll
@@ -340,49 +382,110 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             }
         } else {
             if (tid == 0) {
-                part_ml[2 * (size_t)item] = m_run;
-                part_ml[2 * (size_t)item + 1] = l_run;
+                part_ml[2 * pidx] = m_run;
+                part_ml[2 * pidx + 1] = l_run;
             }
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 const int col = tid + i * kConsumerThreads;
-                if (col < d4) reinterpret_cast<float4*>(part_acc + (size_t)item * d)[col] = acc[i];
+                if (col < d4) reinterpret_cast<float4*>(part_acc + pidx * d)[col] = acc[i];
             }
             if constexpr (FUSED) {
-                // whoever completes the row's last chunk merges the partials
-                __threadfence();
-                named_bar_sync(1, kConsumerThreads);
-                if (tid == 0) scan_tmp[13] = (atomicAdd(&row_done[r], 1) == nchunks - 1) ? 1 : 0;
-                named_bar_sync(1, kConsumerThreads);
-                if (scan_tmp[13]) {
-                    __threadfence();
-                    const size_t first = (size_t)(item - c);
-                    float M = -INFINITY;
-                    for (int i = 0; i < nchunks; ++i) M = fmaxf(M, __ldcg(part_ml + 2 * (first + i)));
-                    float Lsum = 0.f;
-                    for (int i = 0; i < nchunks; ++i)
-                        Lsum += __ldcg(part_ml + 2 * (first + i) + 1) * expf(__ldcg(part_ml + 2 * (first + i)) - M);
-                    const float norm = 1.f / Lsum;
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) {
-                        const int col = tid + i * kConsumerThreads;
-                        if (col < d4) {
-                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                            for (int k = 0; k < nchunks; ++k) {
-                                const float w = expf(__ldcg(part_ml + 2 * (first + k)) - M);
-                                const float4 p = __ldcg(reinterpret_cast<const float4*>(part_acc + (first + k) * d) + col);
-                                a.x = fmaf(w, p.x, a.x); a.y = fmaf(w, p.y, a.y);
-                                a.z = fmaf(w, p.z, a.z); a.w = fmaf(w, p.w, a.w);
-                            }
-                            reinterpret_cast<float4*>(out + (size_t)r * d)[col] =
-                                make_float4(a.x * norm, a.y * norm, a.z * norm, a.w * norm);
-                        }
-                    }
-                    if (tid == 0) row_done[r] = 0;   // ready for the next launch
-                }
+                // merged after the slice has been streamed (at most a head and a tail row per CTA)
+                pend_r[n_pend] = r;
+                pend_nseg[n_pend] = nseg;
+                ++n_pend;
             }
         }
     }
+    if constexpr (FUSED) {
+        // whoever completes a row's last segment merges its partials, in slice order.  Done once,
+        // after streaming, so the fence / atomic / merge latency never stalls the K|V pipeline.
+        if (n_pend > 0) {
+            __threadfence();
+            named_bar_sync(1, kConsumerThreads);
+            if (tid < n_pend) scan_tmp[13 + tid] = (atomicAdd(&row_done[pend_r[tid]], 1) == pend_nseg[tid] - 1) ? 1 : 0;
+            named_bar_sync(1, kConsumerThreads);
+            for (int pi = 0; pi < n_pend; ++pi) {
+                if (!scan_tmp[13 + pi]) continue;
+                __threadfence();
+                const int r = pend_r[pi], nseg = pend_nseg[pi];
+                const int start = pos_first[r];
+                const int b_first = start / quantum;
+                // segment k of the row lives in slice b_first + k: its head slot, except that the
+                // row's first segment is its slice's tail slot unless the row opens that slice
+                auto slot_of = [&](int k) -> size_t {
+                    return (size_t)2 * (b_first + k) + ((k == 0 && start != b_first * quantum) ? 1 : 0);
+                };
+                // (m, l) of up to 32 segments at a time, one per lane: all loads in flight together
+                float M = -INFINITY;
+                for (int k0 = 0; k0 < nseg; k0 += 32) {
+                    const int k = k0 + lane;
+                    float m = (k < nseg) ? __ldcg(part_ml + 2 * slot_of(k)) : -INFINITY;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    M = fmaxf(M, m);
+                }
+                float Lsum = 0.f;
+                float4 a[NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k0 = 0; k0 < nseg; k0 += 32) {
+                    const int k = k0 + lane;
+                    float wl = 0.f, lw = 0.f;
+                    if (k < nseg) {
+                        const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + 2 * slot_of(k)));
+                        wl = expf(ml.x - M);
+                        lw = ml.y * wl;
+                    }
+                    Lsum += warp_sum(lw);
+                    const int kn = min(32, nseg - k0);
+                    for (int kk = 0; kk < kn; kk += 4) {
+                        float4 pv[4][NC];
+                        float w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            w[u] = __shfl_sync(0xffffffffu, wl, min(kk + u, 31));
+                            const size_t sl = slot_of(min(k0 + kk + u, nseg - 1));
+#pragma unroll
+                            for (int i = 0; i < NC; ++i) {
+                                const int col = tid + i * kConsumerThreads;
+                                pv[u][i] = (col < d4 && kk + u < kn)
+                                               ? __ldcg(reinterpret_cast<const float4*>(part_acc + sl * d) + col)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (kk + u < kn) {
+#pragma unroll
+                                for (int i = 0; i < NC; ++i) {
+                                    a[i].x = fmaf(w[u], pv[u][i].x, a[i].x); a[i].y = fmaf(w[u], pv[u][i].y, a[i].y);
+                                    a[i].z = fmaf(w[u], pv[u][i].z, a[i].z); a[i].w = fmaf(w[u], pv[u][i].w, a[i].w);
+                                }
+                            }
+                        }
+                    }
+                }
+                const float norm = 1.f / Lsum;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int col = tid + i * kConsumerThreads;
+                    if (col < d4)
+                        reinterpret_cast<float4*>(out + (size_t)r * d)[col] =
+                            make_float4(a[i].x * norm, a[i].y * norm, a[i].z * norm, a[i].w * norm);
+                }
+                if (tid == 0) row_done[r] = 0;   // ready for the next launch
+            }
+        }
+    }
+    ATTN_STAMP(6);
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[(size_t)blockIdx.x * 8 + 7] = smid;
+    }
+#undef ATTN_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -441,7 +544,7 @@ struct AttnPlan {
     int max_items;
 };
 
-static int plan_attention(mli_ctx* ctx, int B, int S, int d, AttnPlan* p) {
+static int plan_attention(mli_ctx* ctx, int B, int S, int d, bool fused, AttnPlan* p) {
     const int W = S / kPage;
     if (d > 4096) {
         set_error("decode attention: emb_dim > 4096 is not supported by this build");
@@ -454,7 +557,9 @@ static int plan_attention(mli_ctx* ctx, int B, int S, int d, AttnPlan* p) {
     p->G = G;
     const size_t stage_bytes = (size_t)G * 2 * d * 4;
     int ctas = ctx->attn_ctas_per_sm > 0 ? ctx->attn_ctas_per_sm : 2;
-    const size_t budget = (ctas >= 2) ? 100 * 1024 : 200 * 1024;
+    // the fused kernel also keeps the [B+1] position prefix in shared memory
+    const size_t prefix_bytes = fused ? sizeof(int) * ((size_t)B + 1) : 0;
+    const size_t budget = ((ctas >= 2) ? 108 * 1024 : 216 * 1024) - prefix_bytes - 1024;
     int nstage = (int)(budget / stage_bytes);
     if (nstage < 2) nstage = 2;
     if (nstage > kMaxStages) nstage = kMaxStages;
@@ -498,7 +603,7 @@ static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* c
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
     int rc = launch_kernel(ctx, kern, dim3(p.grid), dim3(kAttnThreads), smem, q, page_table, lengths,
                            row_first, item_row, item_chunk, out, part_acc, part_ml, scores_out, row_done,
-                           B, S, d, p.chunk_pages, p.nstage);
+                           B, S, d, p.chunk_pages, p.nstage, reinterpret_cast<long long*>(ctx->tc_dbg));
     if (rc) return rc;
     if (ctx->attn_ev_stop) MLI_CUDA(cudaEventRecord(ctx->attn_ev_stop, ctx->stream));
     return 0;
@@ -508,15 +613,17 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
                                   const int* lengths, float* out, float* softmax_out, int B, int S,
                                   int d) {
     AttnPlan p;
-    int rc = plan_attention(ctx, B, S, d, &p);
-    if (rc) return rc;
     const bool fused = (softmax_out == nullptr) && B <= kMaxFusedRows;
+    int rc = plan_attention(ctx, B, S, d, fused, &p);
+    if (rc) return rc;
     void* meta = nullptr;
     void* part = nullptr;
     void* cnt = nullptr;
     rc = ws_get(ctx, WS_ATTN_META, attention_meta_bytes(B, p.max_items), &meta);
     if (rc) return rc;
-    rc = ws_get(ctx, WS_ATTN_PART, sizeof(float) * ((size_t)p.max_items * (d + 2) + 8), &part);
+    // partial slots: one per (row, chunk) item (legacy) or two per CTA (fused: slice head / tail)
+    const size_t n_part = std::max((size_t)p.max_items, (size_t)2 * p.grid);
+    rc = ws_get(ctx, WS_ATTN_PART, sizeof(float) * (n_part * (d + 2) + 8), &part);
     if (rc) return rc;
     rc = ws_get_zeroed(ctx, WS_ATTN_CNT, sizeof(int) * (size_t)B, &cnt);
     if (rc) return rc;
@@ -525,7 +632,7 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     int* item_chunk = item_row + p.max_items;
     int* row_done = reinterpret_cast<int*>(cnt);
     float* part_ml = reinterpret_cast<float*>(part);
-    float* part_acc = part_ml + 2 * (size_t)p.max_items;
+    float* part_acc = part_ml + 2 * n_part;
     // keep part_acc 16-byte aligned
     part_acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(part_acc) + 15) & ~(uintptr_t)15);
 

@@ -50,16 +50,17 @@ struct SchedArgs {
     float** free_ring;   // [n_blocks]
     int* dec;         // [B][R]
     int* new_idx;     // [B]
-    int* flag_fin;    // [B] scratch
-    int* flag_free;   // [B] scratch
-    int* need_list;   // [B] scratch
-    int* free_rows;   // [B] scratch
-    int* occ;         // [B] scratch
+    // work lists for the model kernels of this step (emitted at the end of the scheduler)
+    int* act_rows;    // [B] rows with length > 0, in row order
+    TileDesc* gran;   // [max_gran] 16-position granules covering [0, L) of every new row
+    int* counts;      // [0] = number of active rows, [1] = number of granules
+    int max_gran;
     volatile int* done_host;  // mapped pinned
     int B, S, W, R, n_blocks, compat;
 };
 
 constexpr int kSchedThreads = 1024;
+constexpr int kGran = kPage;   // positions per prefill granule
 
 // exclusive block scan; every thread must call it.  total = sum over the block.
 __device__ int block_scan_excl(int v, int* total, int* s_warp) {
@@ -89,160 +90,179 @@ __device__ int block_scan_excl(int v, int* total, int* s_warp) {
     return res;
 }
 
+// shared-memory footprint of the scheduler: five int arrays and one pointer array of B entries
+size_t sched_smem_bytes(int B) { return (size_t)B * (5 * sizeof(int) + sizeof(float*)) + 64; }
+
+// One CTA advances the whole continuous-batching state by one iteration.  Per-row state (request
+// of the row, pages of the row, the used-row list) is mirrored in shared memory for the duration of
+// the kernel, and the pages the growth phase hands out come from a shared-memory window of the free
+// ring, so the inherently ordered part of the reference's algorithm (grow in admission order,
+// pre-empt the list tail when the pool is dry) runs without dependent global-memory round trips.
 __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) {
+    extern __shared__ __align__(16) unsigned char sched_smem[];
     __shared__ int s_warp[32];
     __shared__ int s_carry[4];
+    __shared__ SchedVars sv;
     const int tid = threadIdx.x, T = blockDim.x;
-    SchedVars* v = a.v;
     const int B = a.B, S = a.S, W = a.W, R = a.R;
+    float** fq = reinterpret_cast<float**>(sched_smem);          // [B] window of the free ring
+    int* s_req = reinterpret_cast<int*>(fq + B);                  // [B] row -> request (-1 = none)
+    int* s_np = s_req + B;                                        // [B] pages of the row
+    int* s_used = s_np + B;                                       // [B] used-row list
+    int* s_flag = s_used + B;                                     // [B] bit0 finished, bit1 unoccupied; later: occupied
+    int* s_list = s_flag + B;                                     // [B] need list / free rows
     griddep_wait();
     griddep_launch_dependents();
 
-    if (v->done) {
-        __syncthreads();
-        if (tid == 0) v->n_new = 0;
+    if (tid == 0) sv = *a.v;
+    __syncthreads();
+    if (sv.done) {
+        if (tid == 0) {
+            a.v->n_new = 0;
+            a.counts[0] = 0;
+            a.counts[1] = 0;
+        }
         return;
     }
-    const bool first = (v->iter == 0);
+    const bool first = (sv.iter == 0);
+    for (int r = tid; r < B; r += T) {
+        s_req[r] = a.row_req[r];
+        s_np[r] = a.npages[r];
+    }
+    for (int i = tid; i < sv.n_used; i += T) s_used[i] = a.used[i];
     __syncthreads();
+    int n_used = sv.n_used;
+    int F = sv.f_count, fh = sv.f_head, qh = sv.q_head, qc = sv.q_count;
+    const int q_cap = sv.q_cap, nb = a.n_blocks;
 
     if (!first) {
         // ================= phase 1: process_decoder_result (item_storage.cpp:97-139) =================
-        int local_gen = 0;
+        int local_gen = 0, local_err = 0;
         for (int r = tid; r < B; r += T) {
             bool empty = false, finished = false;
-            const int id = a.row_req[r];
+            const int id = s_req[r];
+            int c = (id >= 0) ? a.req_cnt[id] : 0;
             for (int j = 0; j < R; ++j) {
                 const int t = a.dec[(size_t)r * R + j];
                 if (t == MLI_EMPTY_ROW_TOKEN_ID) {
                     empty = true;
                 } else if (id < 0) {
-                    v->error = 1;  // token for a row that is not processing
+                    local_err = 1;  // token for a row that is not processing
                     empty = true;
                 } else {
-                    int c = a.req_cnt[id];
                     if (c < S) a.req_tok[(size_t)id * S + c] = t;
                     c += 1;
-                    a.req_cnt[id] = c;
                     ++local_gen;
                     if (c >= S || t == MLI_EOF_TOKEN_ID) finished = true;
                 }
                 if (finished || empty) break;
             }
-            a.flag_fin[r] = finished ? 1 : 0;
-            a.flag_free[r] = (finished || empty) ? 1 : 0;
+            if (id >= 0) a.req_cnt[id] = (finished && c > S) ? S : c;
+            s_flag[r] = (finished ? 1 : 0) | ((finished || empty) ? 2 : 0);
         }
-        if (local_gen) atomicAdd(reinterpret_cast<unsigned long long*>(&v->generated),
+        if (local_gen) atomicAdd(reinterpret_cast<unsigned long long*>(&a.v->generated),
                                  (unsigned long long)local_gen);
+        if (local_err) a.v->error = 1;
         __syncthreads();
         // finished requests are appended in row order (:118-131)
-        if (tid == 0) s_carry[0] = 0;
-        __syncthreads();
+        int n_fin = sv.n_fin;
         for (int base = 0; base < B; base += T) {
             const int r = base + tid;
-            const int f = (r < B) ? a.flag_fin[r] : 0;
+            const int f = (r < B) ? (s_flag[r] & 1) : 0;
             int tot;
             const int pos = block_scan_excl(f, &tot, s_warp);
             if (f) {
-                const int id = a.row_req[r];
-                if (a.req_cnt[id] > S) a.req_cnt[id] = S;
-                a.fin_ids[v->n_fin + s_carry[0] + pos] = id;
-                a.row_req[r] = -1;
+                a.fin_ids[n_fin + pos] = s_req[r];
+                s_req[r] = -1;
             }
-            __syncthreads();
-            if (tid == 0) s_carry[0] += tot;
-            __syncthreads();
+            n_fin += tot;
         }
-        if (tid == 0) v->n_fin += s_carry[0];
-        __syncthreads();
+        if (tid == 0) a.v->n_fin = n_fin;
 
         // ================= phase 2: free rows in finished_indices (paged_item_storage.cpp:20-32) =====
         {
-            const int n_used = v->n_used;
-            const int f_tail0 = v->f_head + v->f_count;
-            if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
-            __syncthreads();
+            int kept = 0, freed = 0;
             for (int base = 0; base < n_used; base += T) {
                 const int i = base + tid;
                 int row = -1, rel = 0, keep = 0, np = 0;
                 if (i < n_used) {
-                    row = a.used[i];
-                    rel = a.flag_free[row];
+                    row = s_used[i];
+                    rel = (s_flag[row] >> 1) & 1;
                     keep = !rel;
-                    np = rel ? a.npages[row] : 0;
+                    np = rel ? s_np[row] : 0;
                 }
                 int totp, totk;
                 const int ppos = block_scan_excl(np, &totp, s_warp);
                 const int kpos = block_scan_excl(keep, &totk, s_warp);
-                // all reads of used[] in this chunk are done (scan contains barriers)
+                // every read of s_used[] in this chunk is done (the scans contain barriers)
                 if (rel) {
-                    const int o = f_tail0 + s_carry[0] + ppos;
+                    const int o = fh + F + freed + ppos;
                     for (int t = 0; t < np; ++t)
-                        a.free_ring[(o + t) % a.n_blocks] = a.page_table[(size_t)row * W + t];
-                    a.npages[row] = 0;
+                        a.free_ring[(o + t) % nb] = a.page_table[(size_t)row * W + t];
+                    s_np[row] = 0;
                 }
-                if (keep) a.used[s_carry[1] + kpos] = row;
-                __syncthreads();
-                if (tid == 0) { s_carry[0] += totp; s_carry[1] += totk; }
+                if (keep) s_used[kept + kpos] = row;
+                freed += totp;
+                kept += totk;
                 __syncthreads();
             }
-            if (tid == 0) {
-                v->f_count += s_carry[0];
-                v->n_used = s_carry[1];
-            }
-            __syncthreads();
+            F += freed;
+            n_used = kept;
         }
+        __syncthreads();   // ring writes of phase 2 are read back below
 
         // ================= phase 3: grow / pre-empt (paged_item_storage.cpp:36-59) ===================
         {
-            const int n_used = v->n_used;
-            if (tid == 0) s_carry[0] = 0;
-            __syncthreads();
+            int m = 0;
             for (int base = 0; base < n_used; base += T) {
                 const int i = base + tid;
                 int need = 0;
                 if (i < n_used) {
-                    const int row = a.used[i];
-                    const int id = a.row_req[row];
-                    need = (a.req_cnt[id] + R > a.npages[row] * kPage) ? 1 : 0;
+                    const int row = s_used[i];
+                    need = (a.req_cnt[s_req[row]] + R > s_np[row] * kPage) ? 1 : 0;
                 }
                 int tot;
                 const int pos = block_scan_excl(need, &tot, s_warp);
-                if (need) a.need_list[s_carry[0] + pos] = i;
-                __syncthreads();
-                if (tid == 0) s_carry[0] += tot;
-                __syncthreads();
+                if (need) s_list[m + pos] = i;
+                m += tot;
             }
+            // window of the free ring the growth loop may consume: entry j = ring[fh + j]
+            const int n_win = min(F, m);
+            for (int j = tid; j < n_win; j += T) fq[j] = a.free_ring[(fh + j) % nb];
+            __syncthreads();
             if (tid == 0) {
-                const int m = s_carry[0];
-                int n = n_used, F = v->f_count, fh = v->f_head, qh = v->q_head, qc = v->q_count;
+                int n = n_used, taken = 0;   // taken = window entries consumed so far
                 long long pre = 0;
                 auto preempt = [&](int row) {
                     // move_to_new: front of the queue, keeping generated tokens (item_storage.cpp:75-79)
-                    qh = (qh - 1 + v->q_cap) % v->q_cap;
-                    a.queue[qh] = a.row_req[row];
+                    qh = (qh - 1 + q_cap) % q_cap;
+                    a.queue[qh] = s_req[row];
                     ++qc;
-                    a.row_req[row] = -1;
-                    const int np = a.npages[row];
-                    for (int t = 0; t < np; ++t)
-                        a.free_ring[(fh + F + t) % a.n_blocks] = a.page_table[(size_t)row * W + t];
+                    s_req[row] = -1;
+                    const int np = s_np[row];
+                    for (int t = 0; t < np; ++t) {
+                        float* pg = a.page_table[(size_t)row * W + t];
+                        a.free_ring[(fh + F + t) % nb] = pg;
+                        if (taken + F + t < B) fq[taken + F + t] = pg;   // only reachable when F <= m
+                    }
                     F += np;
-                    a.npages[row] = 0;
+                    s_np[row] = 0;
                     ++pre;
                 };
                 for (int k = 0; k < m; ++k) {
-                    const int i = a.need_list[k];
+                    const int i = s_list[k];
                     if (i >= n) break;  // already pre-empted as a tail
-                    const int row = a.used[i];
+                    const int row = s_used[i];
                     for (;;) {
                         if (F > 0) {
                             // allocate_memory_block (:196-203): new page at table index size-1
-                            const int np = a.npages[row];
+                            const int np = s_np[row];
                             if (np < W) {
-                                a.page_table[(size_t)row * W + np] = a.free_ring[fh];
-                                fh = (fh + 1) % a.n_blocks;
+                                a.page_table[(size_t)row * W + np] = fq[taken];
+                                ++taken;
+                                fh = (fh + 1) % nb;
                                 --F;
-                                a.npages[row] = np + 1;
+                                s_np[row] = np + 1;
                             }
                             break;
                         } else if (i == n - 1) {
@@ -250,97 +270,84 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                             --n;
                             break;
                         } else {
-                            preempt(a.used[n - 1]);
+                            preempt(s_used[n - 1]);
                             --n;
                         }
                     }
                 }
-                v->n_used = n;
-                v->f_count = F;
-                v->f_head = fh;
-                v->q_head = qh;
-                v->q_count = qc;
-                v->preemptions += pre;
+                s_carry[0] = n;
+                s_carry[1] = F;
+                s_carry[2] = fh;
+                s_carry[3] = qh;
+                sv.q_count = qc;
+                sv.preemptions += pre;
             }
+            __syncthreads();
+            n_used = s_carry[0];
+            F = s_carry[1];
+            fh = s_carry[2];
+            qh = s_carry[3];
+            qc = sv.q_count;
             __syncthreads();
         }
     }
 
     // ================= phase 4: insert_new_items (paged_item_storage.cpp:62-122) =====================
+    int k_adm = 0;
     {
-        const int n_used = v->n_used;
-        for (int r = tid; r < B; r += T) a.occ[r] = 0;
+        for (int r = tid; r < B; r += T) s_flag[r] = 0;
         __syncthreads();
-        for (int i = tid; i < n_used; i += T) a.occ[a.used[i]] = 1;
+        for (int i = tid; i < n_used; i += T) s_flag[s_used[i]] = 1;
         __syncthreads();
         // unoccupied rows in index order
-        if (tid == 0) s_carry[0] = 0;
-        __syncthreads();
+        int n_free_rows = 0;
         for (int base = 0; base < B; base += T) {
             const int r = base + tid;
-            const int fr = (r < B && !a.occ[r]) ? 1 : 0;
+            const int fr = (r < B && !s_flag[r]) ? 1 : 0;
             int tot;
             const int pos = block_scan_excl(fr, &tot, s_warp);
-            if (fr) a.free_rows[s_carry[0] + pos] = r;
-            __syncthreads();
-            if (tid == 0) s_carry[0] += tot;
-            __syncthreads();
+            if (fr) s_list[n_free_rows + pos] = r;
+            n_free_rows += tot;
         }
-        const int n_free_rows = s_carry[0];
-        const int F = v->f_count, fh = v->f_head, qh = v->q_head, qc = v->q_count;
         const int n_cand = min(n_free_rows, qc);
-        __syncthreads();
         // candidate j takes queue item j; admitted iff cumulative page need <= F (a prefix)
-        if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+        if (tid == 0) s_carry[0] = 0;
         __syncthreads();
+        int need_before = 0;
         for (int base = 0; base < n_cand; base += T) {
             const int j = base + tid;
             int id = -1, len = 0, need = 0;
             if (j < n_cand) {
-                id = a.queue[(qh + j) % v->q_cap];
+                id = a.queue[(qh + j) % q_cap];
                 len = a.req_cnt[id];
                 need = max((len + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
             }
             int totn;
-            const int before = s_carry[0] + block_scan_excl(need, &totn, s_warp);
+            const int before = need_before + block_scan_excl(need, &totn, s_warp);
             const int admit = (j < n_cand && before + need <= F) ? 1 : 0;
             int tota;
             (void)block_scan_excl(admit, &tota, s_warp);
             if (admit) {
-                const int row = a.free_rows[j];
+                const int row = s_list[j];
                 const int np = min(need, W);
                 for (int t = 0; t < np; ++t)
-                    a.page_table[(size_t)row * W + t] = a.free_ring[(fh + before + t) % a.n_blocks];
-                a.npages[row] = np;
+                    a.page_table[(size_t)row * W + t] = a.free_ring[(fh + before + t) % nb];
+                s_np[row] = np;
                 a.lengths[row] = len;
                 a.len_shadow[row] = len;
-                a.row_req[row] = id;
-                a.used[n_used + j] = row;
+                s_req[row] = id;
+                s_used[n_used + j] = row;
                 a.new_idx[j] = row;
+                atomicMax(&s_carry[0], before + need);   // pages consumed by the admitted prefix
             }
-            __syncthreads();
-            if (tid == 0) {
-                // pages consumed by the admitted prefix of this chunk
-                s_carry[1] += tota;
-                s_carry[0] += totn;
-            }
-            __syncthreads();
-        }
-        const int k_adm = s_carry[1];
-        // pages taken = cumulative need of the first k_adm candidates: recompute exactly
-        __syncthreads();
-        if (tid == 0) {
-            int pages = 0;
-            for (int j = 0; j < k_adm; ++j) {
-                const int id = a.queue[(qh + j) % v->q_cap];
-                pages += max((a.req_cnt[id] + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
-            }
-            s_carry[2] = pages;
+            k_adm += tota;
+            need_before += totn;
         }
         __syncthreads();
+        const int pages_taken = s_carry[0];
         // unoccupied rows that got nothing: length 0 (:109-112)
         for (int j = k_adm + tid; j < n_free_rows; j += T) {
-            const int row = a.free_rows[j];
+            const int row = s_list[j];
             a.lengths[row] = 0;
             a.len_shadow[row] = 0;
         }
@@ -348,24 +355,70 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         // quirk Q1 (:113-118): any unoccupied row => the whole stale host array is copied back
         if (a.compat && n_free_rows > 0)
             for (int r = tid; r < B; r += T) a.lengths[r] = a.len_shadow[r];
+        fh = (fh + pages_taken) % nb;
+        F -= pages_taken;
+        qh = (qh + k_adm) % q_cap;
+        qc -= k_adm;
+        n_used += k_adm;
         __syncthreads();
-        if (tid == 0) {
-            v->f_head = (fh + s_carry[2]) % a.n_blocks;
-            v->f_count = F - s_carry[2];
-            v->q_head = (qh + k_adm) % v->q_cap;
-            v->q_count = qc - k_adm;
-            v->n_used = n_used + k_adm;
-            v->n_new = k_adm;
-            v->admitted += k_adm;
-            v->iter += 1;
-            // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
-            if (v->n_used + v->q_count == 0) {
-                v->done = 1;
-                *a.done_host = 1;
-                __threadfence_system();
-            } else {
-                v->steps += 1;
+    }
+
+    // ---- write the mirrors back ----
+    for (int r = tid; r < B; r += T) {
+        a.row_req[r] = s_req[r];
+        a.npages[r] = s_np[r];
+    }
+    for (int i = tid; i < n_used; i += T) a.used[i] = s_used[i];
+
+    // ---- work lists of this step: active rows, prefill granules of the new rows ----
+    int n_act = 0;
+    for (int base = 0; base < B; base += T) {
+        const int r = base + tid;
+        const int on = (r < B && a.lengths[r] > 0) ? 1 : 0;
+        int tot;
+        const int pos = block_scan_excl(on, &tot, s_warp);
+        if (on) a.act_rows[n_act + pos] = r;
+        n_act += tot;
+    }
+    int n_gran = 0;
+    for (int base = 0; base < k_adm; base += T) {
+        const int j = base + tid;
+        int row = -1, n = 0;
+        if (j < k_adm) {
+            row = a.new_idx[j];
+            n = (a.lengths[row] + kGran - 1) / kGran;
+        }
+        int tot;
+        const int pos = block_scan_excl(n, &tot, s_warp);
+        for (int c = 0; c < n; ++c) {
+            if (n_gran + pos + c < a.max_gran) {
+                a.gran[n_gran + pos + c].row = row;
+                a.gran[n_gran + pos + c].j0 = c * kGran;
             }
+        }
+        n_gran += tot;
+    }
+
+    if (tid == 0) {
+        SchedVars* v = a.v;
+        v->f_head = fh;
+        v->f_count = F;
+        v->q_head = qh;
+        v->q_count = qc;
+        v->n_used = n_used;
+        v->n_new = k_adm;
+        v->admitted = sv.admitted + k_adm;
+        v->preemptions = sv.preemptions;
+        v->iter = sv.iter + 1;
+        a.counts[0] = n_act;
+        a.counts[1] = min(n_gran, a.max_gran);
+        // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
+        if (n_used + qc == 0) {
+            v->done = 1;
+            *a.done_host = 1;
+            __threadfence_system();
+        } else {
+            v->steps = sv.steps + 1;
         }
     }
 }
@@ -390,6 +443,8 @@ __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats
         v->n_used = 0; v->n_fin = 0; v->n_new = 0;
         v->iter = 0; v->done = 0; v->error = 0; v->n_req = 0;
         v->steps = 0; v->generated = 0; v->preemptions = 0; v->admitted = 0;
+        a.counts[0] = 0;
+        a.counts[1] = 0;
     }
 }
 
@@ -438,7 +493,10 @@ struct mli_engine {
     cudaEvent_t ev_submit = nullptr, ev_end = nullptr;  // job timing: start of submit .. end of run
     bool submit_timed = false;
     cudaEvent_t ring_ev[4] = {};
-    int* lengths_host = nullptr;  // pinned, profile mode
+    int launches_per_step = 0;     // kernels in the captured step graph
+    cudaEvent_t prof_ev[32] = {};  // profile mode: one event pair per step of a batch
+    int* prof_lengths = nullptr;   // pinned [16][B], profile mode
+    int* lengths_host = nullptr;   // pinned
     // the engine runs on its own non-blocking stream: the caller's stream may be the legacy
     // default stream, which cannot be captured into a graph
     cudaStream_t stream = nullptr;
@@ -479,55 +537,58 @@ int dev_alloc(mli_engine* e, T** out, size_t n) {
     return 0;
 }
 
-// one engine iteration: scheduler, then n_forward_rounds x the model (inference_model.cpp:52-82)
-int enqueue_step(mli_engine* e, bool profile) {
+// the model part of one engine iteration: n_forward_rounds x (encoder -> attention -> decoder)
+// (inference_model.cpp:52-82).  ev0/ev1, when given, bracket the first round's fused attention.
+int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1) {
     mli_ctx* ctx = e->ctx;
     const mli_engine_cfg& c = e->cfg;
     const int B = c.n_batch, S = c.n_sequence, d = c.emb_dim, V = c.n_vocab;
     int rc;
-    // the scheduler is the head of the step: plain launch (fully ordered after the previous step);
-    // everything after it may be chained with programmatic dependent launch
+    // everything after the scheduler may be chained with programmatic dependent launch
     struct PdlScope {
         mli_ctx* c;
         explicit PdlScope(mli_ctx* c_) : c(c_) { c->use_pdl = c->opt_pdl != 0; }
         ~PdlScope() { c->use_pdl = false; }
-    };
-    sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), 0, ctx->stream>>>(e->a);
-    MLI_LAUNCH_CHECK();
-    PdlScope pdl(ctx);
-    if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0, &e->a.v->n_new, e->tiles,
-                                         e->n_tiles, e->max_tiles)))
-        return rc;
-    if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req, e->a.req_tok,
-                                         e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
-                                         e->a.lengths, S, d)))
-        return rc;
-    const bool tc = (ctx->gemm_mode == 0 && ctx->tc_available);
-    if (tc)
-        rc = launch_prefill_kv_paged_tc(ctx, e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
-                                        e->a.lengths, e->wk, e->wv, S, d);
-    else
-        rc = launch_prefill_kv_paged_simt(ctx, e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
-                                          e->a.lengths, e->wk, e->wv, S, d);
-    if (rc) return rc;
+    } pdl(ctx);
+    const bool tc = (ctx->gemm_mode == 0 && ctx->tc_available && d % 128 == 0);
+    if (tc) {
+        // tensor-core mode: the scheduler already listed the active rows and the 16-position prefill
+        // granules of the new rows; encoder -> ONE merged projection (latest K,q,V + prefill K,V)
+        if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req, e->a.req_tok,
+                                             e->a.page_table, e->a.gran, e->a.counts + 1, e->a.max_gran,
+                                             e->a.lengths, S, d, kPage)))
+            return rc;
+    } else {
+        if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0, &e->a.v->n_new, e->tiles,
+                                             e->n_tiles, e->max_tiles)))
+            return rc;
+        if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req, e->a.req_tok,
+                                             e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
+                                             e->a.lengths, S, d)))
+            return rc;
+        if ((rc = launch_prefill_kv_paged_simt(ctx, e->a.page_table, e->tiles, e->n_tiles, e->max_tiles,
+                                               e->a.lengths, e->wk, e->wv, S, d)))
+            return rc;
+    }
     for (int round = 0; round < c.n_forward_rounds; ++round) {
         if (tc)
-            rc = launch_qkv_latest_paged_tc(ctx, e->a.page_table, e->a.lengths, e->wk, e->wq, e->wv,
-                                            e->q_out, B, S, d);
+            rc = launch_step_qkv_tc(ctx, e->a.page_table, e->a.lengths, e->a.act_rows, e->a.counts,
+                                    e->a.gran, e->a.max_gran, round == 0 ? 1 : 0, e->wk, e->wq, e->wv,
+                                    e->q_out, B, S, d);
         else
             rc = launch_qkv_latest_paged_simt(ctx, e->a.page_table, e->a.lengths, e->wk, e->wq, e->wv,
                                               e->q_out, B, S, d);
         if (rc) return rc;
-        if (profile) {
-            ctx->attn_ev_start = e->ev0;
-            ctx->attn_ev_stop = e->ev1;
+        if (round == 0 && ev0) {
+            ctx->attn_ev_start = ev0;
+            ctx->attn_ev_stop = ev1;
         }
         rc = launch_decode_attention_paged(ctx, e->q_out, e->a.page_table, e->a.lengths, e->attn_out,
                                            nullptr, B, S, d);
         ctx->attn_ev_start = ctx->attn_ev_stop = nullptr;
         if (rc) return rc;
-        if (tc)
-            rc = launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d);
+        if (ctx->gemm_mode == 0 && ctx->tc_available)
+            rc = launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d, e->a.act_rows, e->a.counts);
         else
             rc = launch_logits_simt(ctx, e->attn_out, e->emb, e->score, B, V, d);
         if (rc) return rc;
@@ -536,6 +597,14 @@ int enqueue_step(mli_engine* e, bool profile) {
             return rc;
     }
     return 0;
+}
+
+// one engine iteration: scheduler (the head of the step: plain launch, fully ordered after the
+// previous step), then the model
+int enqueue_step(mli_engine* e) {
+    sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), e->ctx->stream>>>(e->a);
+    MLI_LAUNCH_CHECK();
+    return enqueue_model(e, nullptr, nullptr);
 }
 
 void drop_graph(mli_engine* e) {
@@ -559,6 +628,17 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
                 "bad engine dims");
     MLI_REQUIRE(cfg->n_forward_rounds >= 1 && cfg->n_forward_rounds <= kPage,
                 "n_forward_rounds must be 1..16");
+    MLI_REQUIRE(sched_smem_bytes(cfg->n_batch) <= 200 * 1024,
+                "n_batch too large for the device scheduler's shared-memory mirrors (max ~7000 rows per GPU)");
+    {
+        static size_t configured = 48 * 1024;
+        const size_t need = sched_smem_bytes(cfg->n_batch);
+        if (need > configured) {
+            MLI_CUDA(cudaFuncSetAttribute(sched_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)need));
+            configured = need;
+        }
+    }
     mli_engine* e = new mli_engine();
     e->ctx = ctx;
     e->cfg = *cfg;
@@ -584,11 +664,10 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     A(dev_alloc(e, &a.free_ring, cfg->n_blocks));
     A(dev_alloc(e, &a.dec, (size_t)B * R));
     A(dev_alloc(e, &a.new_idx, B));
-    A(dev_alloc(e, &a.flag_fin, B));
-    A(dev_alloc(e, &a.flag_free, B));
-    A(dev_alloc(e, &a.need_list, B));
-    A(dev_alloc(e, &a.free_rows, B));
-    A(dev_alloc(e, &a.occ, B));
+    A(dev_alloc(e, &a.act_rows, B));
+    a.max_gran = B * W;
+    A(dev_alloc(e, &a.gran, (size_t)a.max_gran));
+    A(dev_alloc(e, &a.counts, 4));
     A(dev_alloc(e, &e->q_out, (size_t)B * d));
     A(dev_alloc(e, &e->attn_out, (size_t)B * d));
     A(dev_alloc(e, &e->score, (size_t)B * V));
@@ -637,7 +716,7 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     // it sizes every workspace the captured graph will later hold pointers to.
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(a, e->pool, page_floats, NR);
     MLI_LAUNCH_CHECK();
-    if ((rc = enqueue_step(e, false))) { mli_engine_destroy(e); return rc; }
+    if ((rc = enqueue_step(e))) { mli_engine_destroy(e); return rc; }
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
     *out = e;
@@ -657,6 +736,9 @@ int mli_engine_destroy(mli_engine* e) {
     if (e->stage_buf) cudaFree(e->stage_buf);
     if (e->done_host) cudaFreeHost(e->done_host);
     if (e->lengths_host) cudaFreeHost(e->lengths_host);
+    if (e->prof_lengths) cudaFreeHost(e->prof_lengths);
+    for (auto& ev : e->prof_ev)
+        if (ev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_submit) cudaEventDestroy(e->ev_submit);
@@ -726,71 +808,45 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     e->submit_timed = false;
     long long it = 0;
     if (profile_attention) {
-        // un-captured, synchronous per step: device time of every fused-attention launch plus the
-        // algorithmic bytes it had to move (from the lengths the launch saw)
-        for (;; ++it) {
-            if (max_steps > 0 && it >= max_steps) break;
-            if (*reinterpret_cast<volatile int*>(e->done_host)) break;
-            // lengths as the attention kernel will see them are only known after the scheduler and
-            // the latest-QKV stage; rounds > 1 are profiled on the first round's lengths + round
-            sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), 0, ctx->stream>>>(e->a);
-            MLI_LAUNCH_CHECK();
-            MLI_CUDA(cudaMemcpyAsync(e->lengths_host, e->a.lengths, sizeof(int) * (size_t)B,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-            MLI_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (*reinterpret_cast<volatile int*>(e->done_host)) break;
-            // re-run of the scheduler must not happen: enqueue the rest of the step by hand
-            {
-                const mli_engine_cfg& c = e->cfg;
-                const int S = c.n_sequence, V = c.n_vocab;
-                const bool tc = (ctx->gemm_mode == 0 && ctx->tc_available);
-                if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0,
-                                                     &e->a.v->n_new, e->tiles, e->n_tiles,
-                                                     e->max_tiles)))
-                    return rc;
-                if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req,
-                                                     e->a.req_tok, e->a.page_table, e->tiles,
-                                                     e->n_tiles, e->max_tiles, e->a.lengths, S, d)))
-                    return rc;
-                rc = tc ? launch_prefill_kv_paged_tc(ctx, e->a.page_table, e->tiles, e->n_tiles,
-                                                     e->max_tiles, e->a.lengths, e->wk, e->wv, S, d)
-                        : launch_prefill_kv_paged_simt(ctx, e->a.page_table, e->tiles, e->n_tiles,
-                                                       e->max_tiles, e->a.lengths, e->wk, e->wv, S, d);
-                if (rc) return rc;
-                for (int round = 0; round < c.n_forward_rounds; ++round) {
-                    rc = tc ? launch_qkv_latest_paged_tc(ctx, e->a.page_table, e->a.lengths, e->wk,
-                                                         e->wq, e->wv, e->q_out, B, S, d)
-                            : launch_qkv_latest_paged_simt(ctx, e->a.page_table, e->a.lengths, e->wk,
-                                                           e->wq, e->wv, e->q_out, B, S, d);
-                    if (rc) return rc;
-                    if (round == 0) {
-                        ctx->attn_ev_start = e->ev0;
-                        ctx->attn_ev_stop = e->ev1;
-                    }
-                    rc = launch_decode_attention_paged(ctx, e->q_out, e->a.page_table, e->a.lengths,
-                                                       e->attn_out, nullptr, B, S, d);
-                    ctx->attn_ev_start = ctx->attn_ev_stop = nullptr;
-                    if (rc) return rc;
-                    rc = tc ? launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d)
-                            : launch_logits_simt(ctx, e->attn_out, e->emb, e->score, B, V, d);
-                    if (rc) return rc;
-                    if ((rc = launch_paged_decoder(ctx, e->score, e->a.dec, e->a.lengths,
-                                                   e->a.page_table, e->pos, e->emb, B, V, S, d,
-                                                   c.n_forward_rounds, round)))
-                        return rc;
-                }
+        // un-captured: every fused-attention launch is bracketed by its own pair of CUDA events and
+        // the lengths it saw are copied out (for the algorithmic bytes).  Steps are enqueued in
+        // batches without a host sync in between, so the device stays busy as it does in the graph.
+        constexpr int kBatch = 16;
+        if (!e->prof_ev[0]) {
+            for (auto& ev : e->prof_ev) MLI_CUDA(cudaEventCreate(&ev));
+            MLI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->prof_lengths),
+                                   sizeof(int) * (size_t)B * kBatch, cudaHostAllocDefault));
+        }
+        bool finished = false;
+        while (!finished) {
+            int nb = 0;
+            for (; nb < kBatch; ++nb, ++it) {
+                if (max_steps > 0 && it >= max_steps) { finished = true; break; }
+                sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), ctx->stream>>>(e->a);
+                MLI_LAUNCH_CHECK();
+                MLI_CUDA(cudaMemcpyAsync(e->prof_lengths + (size_t)nb * B, e->a.lengths,
+                                         sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+                if ((rc = enqueue_model(e, e->prof_ev[2 * nb], e->prof_ev[2 * nb + 1]))) return rc;
             }
             MLI_CUDA(cudaStreamSynchronize(ctx->stream));
-            float ms = 0.f;
-            MLI_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-            attn_ms += ms;
-            attn_bytes += attention_algorithmic_bytes(e->lengths_host, B, d);
-            ++attn_launches;
+            for (int k = 0; k < nb; ++k) {
+                const double bytes = attention_algorithmic_bytes(e->prof_lengths + (size_t)k * B, B, d);
+                if (bytes <= 0.0) continue;   // a step past the end of the job: nothing to attend
+                float ms = 0.f;
+                MLI_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]));
+                attn_ms += ms;
+                attn_bytes += bytes;
+                ++attn_launches;
+            }
+            if (*reinterpret_cast<volatile int*>(e->done_host)) finished = true;
         }
     } else {
         if (!e->graph_exec) {
             MLI_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            rc = enqueue_step(e, false);
+            const long long l0 = mli_kernel_launch_count();
+            rc = enqueue_step(e);
+            e->launches_per_step = (int)(mli_kernel_launch_count() - l0);
+            count_launch(-e->launches_per_step);   // captured, not launched
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e->graph);
             if (rc || ce != cudaSuccess) {
                 if (e->graph) cudaGraphDestroy(e->graph);
@@ -807,7 +863,7 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             if (it >= kAhead) MLI_CUDA(cudaEventSynchronize(e->ring_ev[it % kAhead]));
             if (*reinterpret_cast<volatile int*>(e->done_host)) break;
             MLI_CUDA(cudaGraphLaunch(e->graph_exec, ctx->stream));
-            count_launch(4 + 6 * e->cfg.n_forward_rounds);
+            count_launch(e->launches_per_step);
             MLI_CUDA(cudaEventRecord(e->ring_ev[it % kAhead], ctx->stream));
         }
     }

@@ -130,7 +130,7 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-enum TcMode { TC_LATEST = 0, TC_PREFILL = 1, TC_LOGITS = 2 };
+enum TcMode { TC_LATEST = 0, TC_PREFILL = 1, TC_LOGITS = 2, TC_STEP = 3 };
 
 struct TcArgs {
     int mode;
@@ -144,6 +144,10 @@ struct TcArgs {
     float* q_out;          // LATEST
     float* score;          // LOGITS [n_rows][V]
     const float* dense_src;  // LOGITS: activation rows [n_rows][K]
+    const int* act;        // LOGITS (optional) / STEP: compact list of active rows
+    const int* counts;     // [0] = active rows, [1] = granules (device-side)
+    const TileDesc* gran;  // STEP: 16-position prefill granules of the new rows
+    int use_gran;
     int V, W, B;
     int bn;                // activation rows per tile: multiple of 16, <= 256 (the UMMA N)
     int n_stages;          // smem pipeline depth
@@ -195,25 +199,61 @@ struct RowIO {
     const float* src;
     float* dst;
 };
+constexpr int kGranM = kPage;   // positions per granule (STEP mode)
+
+// rows the launch really has (device-side counts where the mode has them)
+__device__ __forceinline__ int tc_n_valid(const TcArgs& args) {
+    int n = args.n_rows;
+    if (args.mode == TC_PREFILL) {
+        n = min(n, *args.n_tiles * kTileM);
+    } else if (args.mode == TC_STEP) {
+        const int pad = (args.counts[0] + 15) & ~15;
+        n = min(n, pad + (args.use_gran ? args.counts[1] * kGranM : 0));
+    } else if (args.mode == TC_LOGITS && args.counts != nullptr) {
+        n = min(n, args.counts[0]);
+    }
+    return n;
+}
+
 __device__ __forceinline__ RowIO row_io(const TcArgs& args, int n, int n_valid, int mat, int f0) {
     RowIO io{nullptr, nullptr};
     if (n >= n_valid) return io;
     if (args.mode == TC_LOGITS) {
-        io.src = args.dense_src + (size_t)n * args.K;
-        io.dst = args.score + (size_t)n * args.V + f0;
+        const int r = args.act ? args.act[n] : n;
+        io.src = args.dense_src + (size_t)r * args.K;
+        io.dst = args.score + (size_t)r * args.V + f0;
         return io;
     }
     int r, j;
+    bool latest = true;
     if (args.mode == TC_LATEST) {
         r = n;
         j = args.lengths[r] - 1;
         if (j < 0) return io;
+    } else if (args.mode == TC_STEP) {
+        const int n_act = args.counts[0];
+        const int pad = (n_act + 15) & ~15;
+        if (n < pad) {
+            if (n >= n_act) return io;
+            r = args.act[n];
+            j = args.lengths[r] - 1;
+            if (j < 0) return io;
+        } else {
+            // earlier positions of a new row; its position L-1 is the row's "latest" entry above
+            const TileDesc t = args.gran[(n - pad) / kGranM];
+            r = t.row;
+            j = t.j0 + ((n - pad) % kGranM);
+            if (j >= args.lengths[r] - 1) return io;
+            latest = false;
+            if (mat == 1) return io;   // no q for prefill positions
+        }
     } else {
         const TileDesc t = args.tiles[n / kTileM];
         r = t.row;
         j = t.j0 + (n % kTileM);
         if (j >= args.lengths[r]) return io;
     }
+    (void)latest;
     float* page = args.page_table[(size_t)r * args.W + j / kPage];
     io.src = page_row_ptr(page, j, args.d, 0);
     io.dst = (mat == 1) ? args.q_out + (size_t)r * args.d + f0
@@ -295,8 +335,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     griddep_wait();
     griddep_launch_dependents();
 
-    int n_valid = args.n_rows;
-    if (args.mode == TC_PREFILL) n_valid = min(n_valid, *args.n_tiles * kTileM);
+    const int n_valid = tc_n_valid(args);
 
     const int num_kb = args.K / kBK;
     const int kb_per = num_kb / split;          // host guarantees divisibility
@@ -795,14 +834,37 @@ int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const Til
     return run_gemm(ctx, w, a, 2 * d / kBM, kMaxBN);
 }
 
-int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V, int d) {
+int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* lengths, const int* act_rows,
+                       const int* counts, const TileDesc* gran, int max_gran, int use_gran,
+                       const float* wk, const float* wq, const float* wv, float* q_output, int B, int S,
+                       int d) {
+    if (!shapes_ok(d, d)) {
+        set_error("tcgen05 step projection: emb_dim must be a multiple of 128");
+        return MLI_ERR_UNSUPPORTED;
+    }
+    OperandEntry* w = nullptr;
+    int rc = get_operand(ctx, wk, wq, wv, 3 * d, d, &w);
+    if (rc) return rc;
+    TcArgs a{};
+    a.mode = TC_STEP; a.K = d; a.d = d; a.page_table = page_table; a.lengths = lengths;
+    a.q_out = q_output; a.W = S / kPage; a.B = B; a.act = act_rows; a.counts = counts; a.gran = gran;
+    a.use_gran = use_gran;
+    const long long bound = (long long)((B + 15) / 16 * 16) + (use_gran ? (long long)max_gran * kGranM : 0);
+    a.n_rows = (int)std::min<long long>(bound, 1 << 30);
+    // a step usually has at most B active rows plus a few short prompts: plan the split for that
+    // and let the clusters walk further tiles when an admission wave brings more
+    return run_gemm(ctx, w, a, 3 * d / kBM, std::max(kMaxBN, (B + 15) / 16 * 16));
+}
+
+int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V, int d,
+                     const int* act_rows, const int* counts) {
     if (!shapes_ok(d, V)) return launch_logits_simt(ctx, attn, emb, score, B, V, d);
     OperandEntry* w = nullptr;
     int rc = get_operand(ctx, emb, nullptr, nullptr, V, d, &w);
     if (rc) return rc;
     TcArgs a{};
     a.mode = TC_LOGITS; a.K = d; a.d = d; a.n_rows = B; a.score = score; a.V = V; a.B = B;
-    a.dense_src = attn;
+    a.dense_src = attn; a.act = act_rows; a.counts = (act_rows != nullptr) ? counts : nullptr;
     return run_gemm(ctx, w, a, V / kBM, 0);
 }
 

@@ -19,11 +19,12 @@ int launch_build_new_row_tiles(mli_ctx* ctx, const int* new_idx, const int* leng
                                const int* n_new_dev, TileDesc* tiles, int* n_tiles, int max_tiles);
 
 // ---- encoder (src/kernels/encoder.cu:102-147 / :56-92) ----------------------------------------
-// tokens come from inp[B,S], or (engine) from req_tok[row_req[r]*S + j] when row_req != nullptr
+// tokens come from inp[B,S], or (engine) from req_tok[row_req[r]*S + j] when row_req != nullptr;
+// tile_m = positions per TileDesc (kTileM, or 16 for the engine's prefill granules)
 int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
                                const int* row_req, const int* req_tok, float* const* page_table,
                                const TileDesc* tiles, const int* n_tiles, int max_tiles,
-                               const int* lengths, int S, int d);
+                               const int* lengths, int S, int d, int tile_m = kTileM);
 int launch_dense_encoder(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
                          float* inp_embedding, const int* lengths, const int* new_idx, int S, int d,
                          int n_new);
@@ -58,8 +59,16 @@ int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const Til
 int launch_qkv_latest_paged_tc(mli_ctx* ctx, float* const* page_table, const int* lengths,
                                const float* wk, const float* wq, const float* wv, float* q_output,
                                int B, int S, int d);
+// act_rows / counts (optional, device): only rows act_rows[0..counts[0]) are computed
 int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V,
-                     int d);
+                     int d, const int* act_rows = nullptr, const int* counts = nullptr);
+// the engine's merged projection: latest-token K,q,V of the active rows AND prefill K,V of the new
+// rows' earlier positions in ONE launch.  act_rows[0..counts[0]) = active rows, gran[0..counts[1]) =
+// 16-position granules of the new rows (ignored when use_gran == 0, i.e. forward rounds > 0).
+int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* lengths, const int* act_rows,
+                       const int* counts, const TileDesc* gran, int max_gran, int use_gran,
+                       const float* wk, const float* wq, const float* wv, float* q_output, int B, int S,
+                       int d);
 
 // ---- fused decode attention --------------------------------------------------------------------
 int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_table,

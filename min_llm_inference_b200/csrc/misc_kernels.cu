@@ -81,7 +81,7 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
                            const int* __restrict__ inp, const int* __restrict__ row_req,
                            const int* __restrict__ req_tok, float* const* __restrict__ page_table,
                            const TileDesc* __restrict__ tiles, const int* __restrict__ n_tiles,
-                           const int* __restrict__ lengths, int S, int d) {
+                           const int* __restrict__ lengths, int S, int d, int tile_m) {
     const int W = S / kPage, d4 = d >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     griddep_wait();
@@ -92,7 +92,7 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
         const int L = lengths[td.row];
         // engine mode: tokens come straight from the device request table (no inp[B,S] copy)
         const int* toks = row_req ? req_tok + (size_t)row_req[td.row] * S : inp + (size_t)td.row * S;
-        for (int m = warp; m < kTileM; m += 8) {
+        for (int m = warp; m < tile_m; m += 8) {
             const int j = td.j0 + m;
             if (j >= L) break;
             const int tok = toks[j];
@@ -111,12 +111,12 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
 int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
                                const int* row_req, const int* req_tok, float* const* page_table,
                                const TileDesc* tiles, const int* n_tiles, int max_tiles,
-                               const int* lengths, int S, int d) {
+                               const int* lengths, int S, int d, int tile_m) {
     int grid = ctx->num_sms * 4;
     if (grid > max_tiles) grid = max_tiles;
     if (grid < 1) grid = 1;
     return launch_kernel(ctx, paged_encoder_tiles_kernel, dim3(grid), dim3(256), 0, emb, pos, inp, row_req,
-                         req_tok, page_table, tiles, n_tiles, lengths, S, d);
+                         req_tok, page_table, tiles, n_tiles, lengths, S, d, tile_m);
 }
 
 // dense encoder (src/kernels/encoder.cu:56-92); element-wise so any emb_dim works

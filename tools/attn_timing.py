@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Phase timing of the fused decode-attention kernel (clock64 stamps written by the kernel) at the
+bench workload's in-job shape: B=256, d=1024, S=128, lengths like a mid-job engine step.
+Diagnostic tool, not a benchmark.      python tools/attn_timing.py [B d S meanL]
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests"))
+import harness as H  # noqa: E402
+import min_llm_inference_b200 as mli  # noqa: E402
+
+NAMES = ["setup+wait", "length scan", "zero-fill", "first data", "main loop(last seg)", "epilogue"]
+
+
+def main():
+    B, d, S, frac = (int(x) for x in sys.argv[1:5]) if len(sys.argv) >= 5 else (256, 1024, 128, 58)
+    torch.cuda.set_device(0)
+    ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(0)
+    L = rng.integers(1, S - 1, size=B).astype(np.int32)
+    L[rng.random(B) > frac / 100.0] = 0          # ~58 % of rows active, as in the bench job
+    case = H.PagedCase(1, B, S, d, L, "Z")
+    pool, tab = case.device(torch)
+    dL = torch.from_numpy(L).cuda()
+    q = (torch.rand((B, d), device="cuda") - 0.5) * 0.1
+    out = torch.empty((B, d), device="cuda")
+    nbytes = float(np.sum((8.0 * d * L + 8.0 * d + 8.0 * ((L + 15) // 16) + 4.0) * (L > 0)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stamps = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
+
+    def run():
+        ctx.call("mli_decode_attention_paged", q, tab, dL, out, None, B, S, d)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    for cold in (False, True):
+        ts = []
+        for _ in range(10):
+            if cold:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = float(np.median(ts))
+        print(f"{'cold L2' if cold else 'warm L2'}: {us:.1f} us/launch (events around one launch), "
+              f"{nbytes / 1e6:.1f} MB algorithmic -> {nbytes / us / 1e3:.0f} GB/s")
+    # back-to-back launches (launch overhead amortised)
+    n = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    print(f"back to back (warm L2): {us:.1f} us/launch -> {nbytes / us / 1e3:.0f} GB/s")
+    flush.zero_()
+    ctx.call("mli_debug_set_gemm_stamps", stamps)
+    run()
+    torch.cuda.synchronize()
+    ctx.call("mli_debug_set_gemm_stamps", None)
+    st = stamps.cpu().numpy()
+    st = st[st[:, 0] != 0]
+    smid = st[:, 7]
+    st = st[:, :7]
+    have = st[:, 4] != 0
+    t_first = (st[have, 4] - st[have, 3]).astype(np.float64)
+    t_main = (st[have, 5] - st[have, 4]).astype(np.float64)
+    t_tot = (st[:, 6] - st[:, 0]).astype(np.float64)
+    print("first-data pct 10/50/90/100:", np.percentile(t_first, [10, 50, 90, 100]).round())
+    print("main loop  pct 10/50/90/100:", np.percentile(t_main, [10, 50, 90, 100]).round())
+    print("total      pct 10/50/90/100:", np.percentile(t_tot, [10, 50, 90, 100]).round())
+    start0 = st[:, 0].min()
+    print("kernel span (first CTA start .. last CTA end, cycles; SM clocks are not synchronised):",
+          int(st[:, 6].max() - start0))
+    order = np.argsort(-t_tot)[:12]
+    print("slowest CTAs (cta, smid, total, first, main):")
+    for i in order:
+        print("   ", i, int(smid[i]), int(t_tot[i]), int(st[i, 4] - st[i, 3]) if st[i, 4] else -1,
+              int(st[i, 5] - st[i, 4]) if st[i, 4] else -1)
+    per_sm = {}
+    for i in range(len(st)):
+        per_sm.setdefault(int(smid[i]), []).append(i)
+    print("CTAs per SM histogram:", np.bincount([len(v) for v in per_sm.values()]))
+    dl = np.diff(st, axis=1).astype(np.float64)
+    print(f"{len(st)} CTAs stamped (cold L2)")
+    for i, nm in enumerate(NAMES):
+        col = dl[:, i]
+        print(f"    {nm:22s} mean {col.mean():8.0f} cyc   min {col.min():8.0f}   max {col.max():8.0f}")
+    tot = (st[:, 6] - st[:, 0]).astype(np.float64)
+    print(f"    {'total in-kernel':22s} mean {tot.mean():8.0f} cyc   max {tot.max():8.0f}")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
