@@ -77,6 +77,10 @@ long long mli_kernel_launch_count(void);
 /* diagnostics (tools/gemm_timing.py): when stamps_dev != NULL every tcgen05 GEMM launch writes
  * clock64() phase stamps [cta][8] into it (>= 8 * 8 * n_ctas bytes); NULL switches it off */
 int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev);
+/* diagnostics (tools/step_timeline.py): when trace_dev != NULL (u64[8 + 8 * capacity], [0] = 0,
+ * [1] = capacity in steps) the kernels of every engine step record the %globaltimer at which their
+ * dependencies were satisfied; must be set before the engine captures its step graph */
+int mli_debug_set_step_trace(mli_ctx* ctx, void* trace_dev);
 
 /* ---- paged stages ------------------------------------------------------------------------ */
 /* replaces launch_paged_attention_encoder_kernel (include/kernels/encoder.h:21-25,

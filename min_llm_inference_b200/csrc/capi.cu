@@ -203,6 +203,12 @@ int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev) {
     return MLI_OK;
 }
 
+int mli_debug_set_step_trace(mli_ctx* ctx, void* trace_dev) {
+    MLI_REQUIRE(ctx, "null ctx");
+    ctx->trace = reinterpret_cast<unsigned long long*>(trace_dev);
+    return MLI_OK;
+}
+
 int mli_ctx_synchronize(mli_ctx* ctx) {
     MLI_REQUIRE(ctx, "null ctx");
     MLI_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -129,6 +129,22 @@ __device__ __forceinline__ void griddep_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// optional in-graph step timeline (tools/step_timeline.py): trace[0] = steps seen so far,
+// trace[1] = capacity in steps, trace[8 + 8*step + slot] = globaltimer (ns) at which kernel `slot`
+// of that step had its dependencies satisfied (i.e. its predecessor had completed).  The scheduler
+// (slot 0) opens a new step.
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+    if (trace == nullptr) return;
+    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) != 0) return;
+    unsigned long long step = trace[0];
+    if (slot == 0) trace[0] = step + 1; else step -= 1;
+    if (step < trace[1]) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        trace[8 + 8 * step + slot] = t;
+    }
+}
+
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -166,6 +182,7 @@ struct mli_ctx {
     int attn_ctas_per_sm = 0;   // 0 = auto
     void* ws[mli::WS_NUM_SLOTS] = {};
     size_t ws_bytes[mli::WS_NUM_SLOTS] = {};
+    unsigned long long* trace = nullptr;  // in-graph step timeline buffer (device), else NULL
     void* tc_dbg = nullptr;     // device buffer for GEMM phase stamps (tools/gemm_timing.py), else NULL
     int opt_pdl = 1;            // MLI_OPT_PDL
     bool use_pdl = false;       // launch_kernel() adds programmatic stream serialization (set by the engine)

@@ -115,7 +115,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         float* __restrict__ out, float* __restrict__ part_acc,
                         float* __restrict__ part_ml, float* __restrict__ scores_out,
                         int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage,
-                        long long* __restrict__ dbg) {
+                        long long* __restrict__ dbg, unsigned long long* trace) {
     // optional phase stamps (tools/attn_timing.py): [cta][8] clock64 of consumer thread 0
 #define ATTN_STAMP(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
     ATTN_STAMP(0);
@@ -145,6 +145,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     __syncthreads();
     griddep_wait();
     griddep_launch_dependents();
+    trace_stamp(trace, 3);
     ATTN_STAMP(1);
 
     int n_items = 0;      // legacy: number of (row, chunk) items
@@ -603,7 +604,7 @@ static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* c
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
     int rc = launch_kernel(ctx, kern, dim3(p.grid), dim3(kAttnThreads), smem, q, page_table, lengths,
                            row_first, item_row, item_chunk, out, part_acc, part_ml, scores_out, row_done,
-                           B, S, d, p.chunk_pages, p.nstage, reinterpret_cast<long long*>(ctx->tc_dbg));
+                           B, S, d, p.chunk_pages, p.nstage, reinterpret_cast<long long*>(ctx->tc_dbg), ctx->trace);
     if (rc) return rc;
     if (ctx->attn_ev_stop) MLI_CUDA(cudaEventRecord(ctx->attn_ev_stop, ctx->stream));
     return 0;

@@ -56,6 +56,7 @@ struct SchedArgs {
     int* counts;      // [0] = number of active rows, [1] = number of granules
     int max_gran;
     volatile int* done_host;  // mapped pinned
+    unsigned long long* trace;  // optional step timeline
     int B, S, W, R, n_blocks, compat;
 };
 
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int* s_list = s_flag + B;                                     // [B] need list / free rows
     griddep_wait();
     griddep_launch_dependents();
+    trace_stamp(a.trace, 0);
 
     if (tid == 0) sv = *a.v;
     __syncthreads();
@@ -602,6 +604,7 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1) {
 // one engine iteration: scheduler (the head of the step: plain launch, fully ordered after the
 // previous step), then the model
 int enqueue_step(mli_engine* e) {
+    e->a.trace = e->ctx->trace;
     sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), e->ctx->stream>>>(e->a);
     MLI_LAUNCH_CHECK();
     return enqueue_model(e, nullptr, nullptr);

@@ -155,6 +155,8 @@ struct TcArgs {
     int acc_stride;        // TMEM columns between accumulators (bn rounded up to 32)
     int tmem_cols;         // power of two >= n_acc * acc_stride
     long long* dbg;        // optional phase stamps
+    unsigned long long* trace;  // optional step timeline
+    int trace_slot;
 };
 
 // optional phase stamps (clock64 of one thread per role) for tools/gemm_timing.py: [cta][8]
@@ -334,6 +336,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
     griddep_wait();
     griddep_launch_dependents();
+    trace_stamp(args.trace, args.trace_slot);
 
     const int n_valid = tc_n_valid(args);
 
@@ -725,6 +728,8 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     if (nst < 2) nst = 2;
     args.n_stages = nst;
     args.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
+    args.trace = ctx->trace;
+    args.trace_slot = (args.mode == TC_LOGITS) ? 4 : 2;
     const size_t smem = tc_smem_bytes(nst, bn);
 
     static bool configured = false;

@@ -81,11 +81,13 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
                            const int* __restrict__ inp, const int* __restrict__ row_req,
                            const int* __restrict__ req_tok, float* const* __restrict__ page_table,
                            const TileDesc* __restrict__ tiles, const int* __restrict__ n_tiles,
-                           const int* __restrict__ lengths, int S, int d, int tile_m) {
+                           const int* __restrict__ lengths, int S, int d, int tile_m,
+                           unsigned long long* trace) {
     const int W = S / kPage, d4 = d >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     griddep_wait();
     griddep_launch_dependents();
+    trace_stamp(trace, 1);
     const int nt = *n_tiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const TileDesc td = tiles[t];
@@ -116,7 +118,7 @@ int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos,
     if (grid > max_tiles) grid = max_tiles;
     if (grid < 1) grid = 1;
     return launch_kernel(ctx, paged_encoder_tiles_kernel, dim3(grid), dim3(256), 0, emb, pos, inp, row_req,
-                         req_tok, page_table, tiles, n_tiles, lengths, S, d, tile_m);
+                         req_tok, page_table, tiles, n_tiles, lengths, S, d, tile_m, ctx->trace);
 }
 
 // dense encoder (src/kernels/encoder.cu:56-92); element-wise so any emb_dim works
@@ -158,11 +160,13 @@ __global__ void __launch_bounds__(256)
 decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result,
                int* __restrict__ lengths, float* const* __restrict__ page_table,
                float* __restrict__ inp_embedding, const float* __restrict__ pos,
-               const float* __restrict__ emb, int V, int S, int d, int n_dec, int i_dec) {
+               const float* __restrict__ emb, int V, int S, int d, int n_dec, int i_dec,
+               unsigned long long* trace) {
     const int r = blockIdx.x;
     const int tid = threadIdx.x;
     griddep_wait();
     griddep_launch_dependents();
+    trace_stamp(trace, 5);
     const int L = lengths[r];
     if (L == 0) {
         if (tid == 0) decoder_result[(size_t)r * n_dec + i_dec] = MLI_EMPTY_ROW_TOKEN_ID;
@@ -217,14 +221,15 @@ int launch_paged_decoder(mli_ctx* ctx, const float* score, int* decoder_result, 
                          float* const* page_table, const float* pos, const float* emb, int B, int V,
                          int S, int d, int n_dec, int i_dec) {
     return launch_kernel(ctx, decoder_kernel<true>, dim3(B), dim3(256), 0, score, decoder_result, lengths,
-                         page_table, static_cast<float*>(nullptr), pos, emb, V, S, d, n_dec, i_dec);
+                         page_table, static_cast<float*>(nullptr), pos, emb, V, S, d, n_dec, i_dec, ctx->trace);
 }
 
 int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
                          float* inp_embedding, const float* pos, const float* emb, int B, int V, int S,
                          int d) {
     return launch_kernel(ctx, decoder_kernel<false>, dim3(B), dim3(256), 0, score, decoder_result, lengths,
-                         static_cast<float* const*>(nullptr), inp_embedding, pos, emb, V, S, d, 1, 0);
+                         static_cast<float* const*>(nullptr), inp_embedding, pos, emb, V, S, d, 1, 0,
+                         static_cast<unsigned long long*>(nullptr));
 }
 
 }  // namespace mli

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""In-graph timeline of the engine step on the bench workload (BASELINE configs[1]): every kernel of
+the captured step graph records %globaltimer once its dependencies are satisfied, so consecutive
+stamps give the time each kernel (plus its launch gap) really takes inside the graph -- which ncu's
+serialised, cold-cache per-kernel durations cannot show.  Diagnostic tool, not a benchmark.
+
+    python tools/step_timeline.py [--pdl 0|1] [--out profiles/xyz.md]
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests"))
+import harness as H  # noqa: E402
+import min_llm_inference_b200 as mli  # noqa: E402
+from bench import WORKLOAD  # noqa: E402
+
+SLOTS = ["sched_step", "encoder", "QKV+prefill GEMM", "decode attention", "logits GEMM", "decoder"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    wl = WORKLOAD
+    B, S, d, V = wl["B"], wl["S"], wl["d"], wl["V"]
+    torch.cuda.set_device(0)
+    ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
+    ctx.set_option(mli.OPT_PDL, args.pdl)
+    cap = 4096
+    trace = torch.zeros(8 + 8 * cap, dtype=torch.int64, device="cuda")
+    trace[1] = cap
+    ctx.call("mli_debug_set_step_trace", trace)
+    w = H.make_weights(1001, d, V, S, "Z")
+    offs, toks = H.make_prompts(2002, wl["n_req"], wl["lo"], wl["hi"])
+    dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None)
+    eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+    d_offs, d_toks = torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda()
+    for _ in range(2):
+        eng.submit(d_offs, d_toks, is_device=True)
+        eng.run()
+    torch.cuda.synchronize()
+    trace[0] = 0
+    trace[8:] = 0
+    torch.cuda.synchronize()
+    eng.submit(d_offs, d_toks, is_device=True)
+    eng.run()
+    st = eng.stats()
+    torch.cuda.synchronize()
+    t = trace.cpu().numpy()
+    n = int(min(t[0], cap))
+    tl = t[8:8 + 8 * n].reshape(n, 8)[:, :6].astype(np.float64)
+    real = int(st.steps)
+    # duration of kernel k of step i = stamp of the next kernel - its own stamp
+    nxt = np.concatenate([tl[:, 1:], np.vstack([tl[1:, :1], [[np.nan]]])], axis=1)
+    dur = (nxt - tl)[:real - 1] / 1e3
+    lines = [f"# In-graph step timeline, bench workload (B={B}, d={d}, S={S}), pdl={args.pdl}",
+             "",
+             f"{real} engine iterations, {st.generated_tokens} tokens, device job time {st.gpu_ms:.2f} ms "
+             f"({1e3 * st.gpu_ms / real:.1f} us / iteration).  Stamp = %globaltimer when the kernel's "
+             "dependencies were satisfied; a kernel's time = next stamp - its stamp (includes the launch gap).",
+             "",
+             "| kernel | mean us | median us | p90 us | share |", "|---|---:|---:|---:|---:|"]
+    tot = np.nansum(np.nanmean(dur, axis=0))
+    for k, name in enumerate(SLOTS):
+        col = dur[:, k]
+        col = col[~np.isnan(col)]
+        lines.append(f"| {name} | {col.mean():.1f} | {np.median(col):.1f} | {np.percentile(col, 90):.1f} | "
+                     f"{100 * col.mean() / tot:.1f}% |")
+    lines.append(f"\nSum of means {tot:.1f} us per iteration.")
+    text = "\n".join(lines)
+    print(text)
+    if args.out:
+        Path(args.out).write_text(text + "\n")
+    eng.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
