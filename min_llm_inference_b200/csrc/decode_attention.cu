@@ -99,6 +99,9 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // FUSED = false: (row, chunk) items from attn_prep_kernel, merge by attn_combine_kernel -- used when
 // the [B,S] probabilities are requested or B is too large for the shared-memory prefix.
 constexpr int kMaxFusedRows = 4096;
+constexpr int kMaxPend = 32;
+constexpr int kMinDynFair = 256;   // positions per CTA below which all slices are static
+constexpr int kAttnCtrlInts = 16 + kMaxStages + 3 * kMaxPend;
 
 struct AttnSeg {
     int r;        // batch row
@@ -128,8 +131,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_floats);
     uint64_t* empty_bar = full_bar + kMaxStages;
     float* red = reinterpret_cast<float*>(empty_bar + kMaxStages);  // [2][kConsumerWarps][G]
-    int* scan_tmp = reinterpret_cast<int*>(red + 2 * kConsumerWarps * G);   // [16]: warp totals, carry, flag
-    int* pos_first = scan_tmp + 16;                                          // FUSED: [B + 1]
+    int* scan_tmp = reinterpret_cast<int*>(red + 2 * kConsumerWarps * G);   // [16]: warp totals, carry
+    int* stage_meta = scan_tmp + 16;                                         // [kMaxStages] slice opened by a stage
+    int* pend_r = stage_meta + kMaxStages;                                   // [kMaxPend] partial rows to merge
+    int* pend_nseg = pend_r + kMaxPend;
+    int* pend_flag = pend_nseg + kMaxPend;
+    int* pos_first = pend_flag + kMaxPend;                                   // FUSED: [B + 1]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -149,8 +156,10 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     ATTN_STAMP(1);
 
     int n_items = 0;      // legacy: number of (row, chunk) items
-    int quantum = 0;      // fused: positions per CTA
-    int g0 = 0, g1 = 0;   // fused: this CTA's slice of the flattened position space
+    // fused: the flattened position space [0, P) is cut into gridDim.x STATIC slices of qs positions
+    // (CTA b starts with slice b: ~3/4 of a fair share) followed by DYNAMIC slices of qd positions
+    // that CTAs claim from a global counter as they run dry -- faster SMs take more of the tail.
+    int qs = 1, qd = 1, dyn0 = 0, n_slices = 0, P = 0;
     if constexpr (FUSED) {
         // exclusive prefix of the lengths, kAttnThreads rows at a time
         if (tid == 0) scan_tmp[12] = 0;
@@ -173,16 +182,29 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             if (tid == kAttnThreads - 1) scan_tmp[12] = before + v;
             __syncthreads();
         }
-        const int P = scan_tmp[12];
+        P = scan_tmp[12];
         if (tid == 0) pos_first[B] = P;
         __syncthreads();
-        quantum = (P + (int)gridDim.x - 1) / (int)gridDim.x;
-        quantum = max(G, (quantum + G - 1) / G * G);
-        g0 = min(P, (int)blockIdx.x * quantum);
-        g1 = min(P, g0 + quantum);
+        const int grid = (int)gridDim.x;
+        const int fair = (P + grid - 1) / grid;
+        // small problems (a fair share of a few dozen positions) are split statically: dynamic
+        // slices would be a single pipeline stage each and their claims / merges cost more than
+        // the tail they remove
+        qs = (fair >= kMinDynFair) ? max(G, (fair * 3 / 4) / G * G) : max(G, (fair + G - 1) / G * G);
+        dyn0 = (int)min((long long)P, (long long)grid * qs);
+        const int dyn = P - dyn0;
+        qd = max(G, ((dyn + 3 * grid - 1) / (3 * grid) + G - 1) / G * G);
+        n_slices = grid + (dyn + qd - 1) / qd;
     } else {
         n_items = row_first_g[B];
     }
+    auto slice_start = [&](int sl) -> int {
+        return sl < (int)gridDim.x ? min(P, sl * qs) : min(P, dyn0 + (sl - (int)gridDim.x) * qd);
+    };
+    auto slice_of = [&](int pos) -> int {
+        return pos < dyn0 ? pos / qs : (int)gridDim.x + (pos - dyn0) / qd;
+    };
+    int slice = 0, g0 = 0, g1 = 0;   // fused: current slice and its position range
 
     // work iterator, identical in the producer and the consumers.  `cur` is a global position
     // (fused) or an item index (legacy).
@@ -198,8 +220,8 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             sg.r = lo;
             sg.p0 = cur - start;
             sg.p1 = min(g1 - start, L);
-            sg.nseg = (start + L - 1) / quantum - start / quantum + 1;
-            sg.pidx = 2 * (int)blockIdx.x + (cur == g0 ? 0 : 1);
+            sg.nseg = slice_of(start + L - 1) - slice_of(start) + 1;
+            sg.pidx = 2 * slice + (cur == g0 ? 0 : 1);
             cur = start + sg.p1;
             return true;
         } else {
@@ -215,42 +237,71 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             return true;
         }
     };
-    int cur = FUSED ? g0 : (int)blockIdx.x;
+    int cur = (int)blockIdx.x;   // legacy: first item
     AttnSeg sg;
     ATTN_STAMP(2);
 
     if (warp == kConsumerWarps) {
         // ===================== producer warp =====================
         uint32_t it = 0;  // running stage counter across segments
-        while (next_seg(cur, sg)) {
-            const int r = sg.r, p1 = sg.p1;
-            // page pointers are fetched 32 pages at a time: lane i holds page (pgb + i)
-            int pgb = -(1 << 30);
-            const float* my_page = nullptr;
-            for (int pos = sg.p0; pos < p1; pos += G, ++it) {
+        slice = (int)blockIdx.x;
+        for (;;) {
+            bool open_slice = false;
+            if constexpr (FUSED) {
+                if (slice >= n_slices) break;
+                g0 = slice_start(slice);
+                g1 = slice_start(slice + 1);
+                cur = g0;
+                open_slice = true;
+            }
+            while (next_seg(cur, sg)) {
+                const int r = sg.r, p1 = sg.p1;
+                // page pointers are fetched 32 pages at a time: lane i holds page (pgb + i)
+                int pgb = -(1 << 30);
+                const float* my_page = nullptr;
+                for (int pos = sg.p0; pos < p1; pos += G, ++it) {
+                    const int stage = it % nstage;
+                    const uint32_t parity = (it / nstage) & 1u;
+                    const int nvalid = min(G, p1 - pos);
+                    if (pos / kPage < pgb || (pos + nvalid - 1) / kPage >= pgb + 32) {
+                        pgb = pos / kPage;
+                        const int pg = pgb + lane;
+                        my_page = (pg * kPage < p1) ? page_table[(size_t)r * W + pg] : nullptr;
+                    }
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[stage], parity ^ 1u);
+                        // the first stage of a slice tells the consumers which slice it opens
+                        if (open_slice) stage_meta[stage] = slice;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)nvalid * row_floats * 4u);
+                    }
+                    open_slice = false;
+                    __syncwarp();
+                    // lane g copies position pos+g (K|V rows are contiguous: 8*d bytes)
+                    const int j = pos + (lane < G ? lane : 0);
+                    const int pg = min(j / kPage - pgb, 31);
+                    const float* page = reinterpret_cast<const float*>(
+                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_page), pg));
+                    if (lane < nvalid) {
+                        const float* src = page + (size_t)(j & (kPage - 1)) * 3 * d + d;
+                        bulk_g2s(ring + (size_t)stage * stage_floats + (size_t)lane * row_floats, src,
+                                 (uint32_t)row_floats * 4u, &full_bar[stage]);
+                    }
+                }
+            }
+            if constexpr (!FUSED) break;
+            if (n_slices == (int)gridDim.x) break;   // no dynamic slices in this launch
+            // next slice: claim a dynamic one
+            int nxt = 0;
+            if (lane == 0) nxt = (int)gridDim.x + atomicAdd(&row_done[B], 1);
+            slice = __shfl_sync(0xffffffffu, nxt, 0);
+        }
+        if constexpr (FUSED) {
+            // end-of-work marker: a data-less stage whose meta is -1
+            if (lane == 0) {
                 const int stage = it % nstage;
-                const uint32_t parity = (it / nstage) & 1u;
-                const int nvalid = min(G, p1 - pos);
-                if (pos / kPage < pgb || (pos + nvalid - 1) / kPage >= pgb + 32) {
-                    pgb = pos / kPage;
-                    const int pg = pgb + lane;
-                    my_page = (pg * kPage < p1) ? page_table[(size_t)r * W + pg] : nullptr;
-                }
-                if (lane == 0) {
-                    mbar_wait(&empty_bar[stage], parity ^ 1u);
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)nvalid * row_floats * 4u);
-                }
-                __syncwarp();
-                // lane g copies position pos+g (K|V rows are contiguous: 8*d bytes)
-                const int j = pos + (lane < G ? lane : 0);
-                const int pg = min(j / kPage - pgb, 31);
-                const float* page = reinterpret_cast<const float*>(
-                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_page), pg));
-                if (lane < nvalid) {
-                    const float* src = page + (size_t)(j & (kPage - 1)) * 3 * d + d;
-                    bulk_g2s(ring + (size_t)stage * stage_floats + (size_t)lane * row_floats, src,
-                             (uint32_t)row_floats * 4u, &full_bar[stage]);
-                }
+                mbar_wait(&empty_bar[stage], ((it / nstage) & 1u) ^ 1u);
+                stage_meta[stage] = -1;
+                mbar_arrive(&full_bar[stage]);
             }
         }
         return;
@@ -267,157 +318,76 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         }
     }
     uint32_t it = 0;
-    int pend_r[2], pend_nseg[2], n_pend = 0;   // partial rows of this slice (head, tail)
-    ATTN_STAMP(3);
-    while (next_seg(cur, sg)) {
-        const int r = sg.r, p0 = sg.p0, p1 = sg.p1;
-
-        float4 qv[NC];
-        float4 acc[NC];
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            const int col = tid + i * kConsumerThreads;
-            qv[i] = (col < d4) ? reinterpret_cast<const float4*>(q + (size_t)r * d)[col]
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float m_run = -INFINITY, l_run = 0.f;
-
-        for (int pos = p0; pos < p1; pos += G, ++it) {
-            const int stage = it % nstage;
-            const uint32_t parity = (it / nstage) & 1u;
-            const int nvalid = min(G, p1 - pos);
-            const float* sbase = ring + (size_t)stage * stage_floats;
-            float* red_buf = red + (size_t)(it & 1u) * kConsumerWarps * G;
-            mbar_wait(&full_bar[stage], parity);
-            if (it == 0) ATTN_STAMP(4);
-
-            // ---- phase A: partial q.K over this thread's columns, warp reduce ----
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float s = 0.f;
-                if (g < nvalid) {
-                    const float4* krow = reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats);
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) {
-                        const int col = tid + i * kConsumerThreads;
-                        if (col < d4) {
-                            const float4 k = krow[col];
-                            s = fmaf(qv[i].x, k.x, s);
-                            s = fmaf(qv[i].y, k.y, s);
-                            s = fmaf(qv[i].z, k.z, s);
-                            s = fmaf(qv[i].w, k.w, s);
-                        }
-                    }
-                }
-                s = warp_sum(s);
-                if (lane == 0) red_buf[warp * G + g] = s;
-            }
+    // Partial rows are merged by whoever completes a row's last segment, in slice order.  The
+    // fence / atomic / merge latency is kept off the K|V pipeline: rows are queued and flushed after
+    // the CTA has run out of slices (or when the queue is full).
+    int n_pend = 0;
+    auto flush_pending = [&]() {
+        if constexpr (FUSED) {
+            if (n_pend == 0) return;
+            // release: the CTA barrier orders every consumer thread's partial stores before the
+            // gpu-scope acq_rel atomic of the arriving thread (cumulativity); acquire: the same
+            // atomic, then the barrier, then L1-bypassing loads (__ldcg) by all threads
             named_bar_sync(1, kConsumerThreads);
-
-            // ---- every thread rebuilds the G scores identically ----
-            float sc[G];
-            float m_new = m_run;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < kConsumerWarps; ++w) s += red_buf[w * G + g];
-                s = s / sqrt_d;
-                sc[g] = s;
-                if (g < nvalid) m_new = fmaxf(m_new, s);
-            }
-            if (scores_out != nullptr) {
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                    if (tid == g && g < nvalid) scores_out[(size_t)r * S + pos + g] = sc[g];
-            }
-            const float corr = expf(m_run - m_new);  // exp(-inf) = 0 on the first stage
-            l_run *= corr;
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr;
-            }
-            // ---- phase B: P.V ----
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if (g < nvalid) {
-                    const float p = expf(sc[g] - m_new);
-                    l_run += p;
-                    const float4* vrow =
-                        reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats + d);
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) {
-                        const int col = tid + i * kConsumerThreads;
-                        if (col < d4) {
-                            const float4 v = vrow[col];
-                            acc[i].x = fmaf(p, v.x, acc[i].x);
-                            acc[i].y = fmaf(p, v.y, acc[i].y);
-                            acc[i].z = fmaf(p, v.z, acc[i].z);
-                            acc[i].w = fmaf(p, v.w, acc[i].w);
-                        }
-                    }
-                }
-            }
-            m_run = m_new;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        }
-
-        // ---- segment epilogue ----
-        ATTN_STAMP(5);
-        const int nseg = sg.nseg;
-        const size_t pidx = (size_t)sg.pidx;
-        if (nseg == 1) {
-            if (!FUSED && tid == 0) {
-                part_ml[2 * pidx] = m_run;
-                part_ml[2 * pidx + 1] = l_run;
-            }
-            const float norm = 1.f / l_run;
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const int col = tid + i * kConsumerThreads;
-                if (col < d4)
-                    reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(
-                        acc[i].x * norm, acc[i].y * norm, acc[i].z * norm, acc[i].w * norm);
-            }
-        } else {
-            if (tid == 0) {
-                part_ml[2 * pidx] = m_run;
-                part_ml[2 * pidx + 1] = l_run;
-            }
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const int col = tid + i * kConsumerThreads;
-                if (col < d4) reinterpret_cast<float4*>(part_acc + pidx * d)[col] = acc[i];
-            }
-            if constexpr (FUSED) {
-                // merged after the slice has been streamed (at most a head and a tail row per CTA)
-                pend_r[n_pend] = r;
-                pend_nseg[n_pend] = nseg;
-                ++n_pend;
-            }
-        }
-    }
-    if constexpr (FUSED) {
-        // whoever completes a row's last segment merges its partials, in slice order.  Done once,
-        // after streaming, so the fence / atomic / merge latency never stalls the K|V pipeline.
-        if (n_pend > 0) {
-            __threadfence();
-            named_bar_sync(1, kConsumerThreads);
-            if (tid < n_pend) scan_tmp[13 + tid] = (atomicAdd(&row_done[pend_r[tid]], 1) == pend_nseg[tid] - 1) ? 1 : 0;
+            if (tid < n_pend)
+                pend_flag[tid] = (atom_add_acq_rel_gpu(&row_done[pend_r[tid]], 1) == pend_nseg[tid] - 1) ? 1 : 0;
             named_bar_sync(1, kConsumerThreads);
             for (int pi = 0; pi < n_pend; ++pi) {
-                if (!scan_tmp[13 + pi]) continue;
-                __threadfence();
+                if (!pend_flag[pi]) continue;
                 const int r = pend_r[pi], nseg = pend_nseg[pi];
                 const int start = pos_first[r];
-                const int b_first = start / quantum;
+                const int b_first = slice_of(start);
                 // segment k of the row lives in slice b_first + k: its head slot, except that the
                 // row's first segment is its slice's tail slot unless the row opens that slice
                 auto slot_of = [&](int k) -> size_t {
-                    return (size_t)2 * (b_first + k) + ((k == 0 && start != b_first * quantum) ? 1 : 0);
+                    return (size_t)2 * (b_first + k) + ((k == 0 && start != slice_start(b_first)) ? 1 : 0);
                 };
+                if (nseg <= 4) {
+                    // common case: every load of the merge is issued before anything is consumed
+                    float2 ml[4];
+                    float4 pv[4][NC];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const size_t sl = slot_of(min(u, nseg - 1));
+                        ml[u] = __ldcg(reinterpret_cast<const float2*>(part_ml + 2 * sl));
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            const int col = tid + i * kConsumerThreads;
+                            pv[u][i] = (col < d4) ? __ldcg(reinterpret_cast<const float4*>(part_acc + sl * d) + col)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    float M = ml[0].x;
+#pragma unroll
+                    for (int u = 1; u < 4; ++u)
+                        if (u < nseg) M = fmaxf(M, ml[u].x);
+                    float Lsum = 0.f;
+                    float4 a[NC];
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (u < nseg) {
+                            const float w = expf(ml[u].x - M);
+                            Lsum += ml[u].y * w;
+#pragma unroll
+                            for (int i = 0; i < NC; ++i) {
+                                a[i].x = fmaf(w, pv[u][i].x, a[i].x); a[i].y = fmaf(w, pv[u][i].y, a[i].y);
+                                a[i].z = fmaf(w, pv[u][i].z, a[i].z); a[i].w = fmaf(w, pv[u][i].w, a[i].w);
+                            }
+                        }
+                    }
+                    const float norm = 1.f / Lsum;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int col = tid + i * kConsumerThreads;
+                        if (col < d4)
+                            reinterpret_cast<float4*>(out + (size_t)r * d)[col] =
+                                make_float4(a[i].x * norm, a[i].y * norm, a[i].z * norm, a[i].w * norm);
+                    }
+                    if (tid == 0) row_done[r] = 0;   // ready for the next launch
+                    continue;
+                }
                 // (m, l) of up to 32 segments at a time, one per lane: all loads in flight together
                 float M = -INFINITY;
                 for (int k0 = 0; k0 < nseg; k0 += 32) {
@@ -476,7 +446,175 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         reinterpret_cast<float4*>(out + (size_t)r * d)[col] =
                             make_float4(a[i].x * norm, a[i].y * norm, a[i].z * norm, a[i].w * norm);
                 }
+
                 if (tid == 0) row_done[r] = 0;   // ready for the next launch
+            }
+            named_bar_sync(1, kConsumerThreads);
+            n_pend = 0;
+        }
+    };
+    ATTN_STAMP(3);
+    for (;;) {
+    if constexpr (FUSED) {
+        // the next stage of the ring opens a slice (or ends the work): learn which
+        const int stage = it % nstage;
+        mbar_wait(&full_bar[stage], (it / nstage) & 1u);
+        slice = stage_meta[stage];
+        if (slice < 0) break;
+        g0 = slice_start(slice);
+        g1 = slice_start(slice + 1);
+        cur = g0;
+        if (n_pend + 2 > kMaxPend) flush_pending();
+    }
+    while (next_seg(cur, sg)) {
+        const int r = sg.r, p0 = sg.p0, p1 = sg.p1;
+
+        float4 qv[NC];
+        float4 acc[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int col = tid + i * kConsumerThreads;
+            qv[i] = (col < d4) ? reinterpret_cast<const float4*>(q + (size_t)r * d)[col]
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float m_run = -INFINITY, l_run = 0.f;
+
+        for (int pos = p0; pos < p1; pos += G, ++it) {
+            const int stage = it % nstage;
+            const uint32_t parity = (it / nstage) & 1u;
+            const int nvalid = min(G, p1 - pos);
+            const float* sbase = ring + (size_t)stage * stage_floats;
+            float* red_buf = red + (size_t)(it & 1u) * kConsumerWarps * G;
+            mbar_wait(&full_bar[stage], parity);
+            if (it == 0) ATTN_STAMP(4);
+
+            // ---- phase A: partial q.K over this thread's columns, warp reduce ----
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float s = 0.f;
+                if (g < nvalid) {
+                    const float4* krow = reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int col = tid + i * kConsumerThreads;
+                        if (col < d4) {
+                            const float4 k = krow[col];
+                            s = fmaf(qv[i].x, k.x, s);
+                            s = fmaf(qv[i].y, k.y, s);
+                            s = fmaf(qv[i].z, k.z, s);
+                            s = fmaf(qv[i].w, k.w, s);
+                        }
+                    }
+                }
+                s = warp_sum(s);
+                if (lane == 0) red_buf[warp * G + g] = s;
+            }
+            named_bar_sync(1, kConsumerThreads);
+
+            // ---- scores: each warp reduces the 8 x G warp partials with shuffles.  Lane l ends up
+            // with the score of position g = l % G, so the division, the running max and the
+            // exponentials are computed once per lane instead of G times per thread ----
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < (kConsumerWarps * G + 31) / 32; ++i) {
+                const int idx = lane + 32 * i;
+                if (idx < kConsumerWarps * G) tot += red_buf[idx];   // idx = w * G + g, 32 % G == 0
+            }
+#pragma unroll
+            for (int o = G; o < 32 && o < kConsumerWarps * G; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const int myg = lane % G;
+            tot = __shfl_sync(0xffffffffu, tot, myg);   // lanes >= 8 * G took no part in the reduction
+            const float sc = tot / sqrt_d;
+            float m_stage = (myg < nvalid) ? sc : -INFINITY;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) m_stage = fmaxf(m_stage, __shfl_xor_sync(0xffffffffu, m_stage, o));
+            const float m_new = fmaxf(m_run, m_stage);
+            if (scores_out != nullptr) {
+                if (tid < G && tid < nvalid) scores_out[(size_t)r * S + pos + tid] = sc;
+            }
+            const float corr = expf(m_run - m_new);  // exp(-inf) = 0 on the first stage
+            const float p_mine = (myg < nvalid) ? expf(sc - m_new) : 0.f;
+            float p_sum = p_mine;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+            l_run = l_run * corr + p_sum;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr;
+            }
+            // ---- phase B: P.V ----
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float p = __shfl_sync(0xffffffffu, p_mine, g);
+                if (g < nvalid) {
+                    const float4* vrow =
+                        reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats + d);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int col = tid + i * kConsumerThreads;
+                        if (col < d4) {
+                            const float4 v = vrow[col];
+                            acc[i].x = fmaf(p, v.x, acc[i].x);
+                            acc[i].y = fmaf(p, v.y, acc[i].y);
+                            acc[i].z = fmaf(p, v.z, acc[i].z);
+                            acc[i].w = fmaf(p, v.w, acc[i].w);
+                        }
+                    }
+                }
+            }
+            m_run = m_new;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        }
+
+        // ---- segment epilogue ----
+        ATTN_STAMP(5);
+        const int nseg = sg.nseg;
+        const size_t pidx = (size_t)sg.pidx;
+        if (nseg == 1) {
+            if (!FUSED && tid == 0) {
+                part_ml[2 * pidx] = m_run;
+                part_ml[2 * pidx + 1] = l_run;
+            }
+            const float norm = 1.f / l_run;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int col = tid + i * kConsumerThreads;
+                if (col < d4)
+                    reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(
+                        acc[i].x * norm, acc[i].y * norm, acc[i].z * norm, acc[i].w * norm);
+            }
+        } else {
+            if (tid == 0) {
+                part_ml[2 * pidx] = m_run;
+                part_ml[2 * pidx + 1] = l_run;
+            }
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int col = tid + i * kConsumerThreads;
+                if (col < d4) reinterpret_cast<float4*>(part_acc + pidx * d)[col] = acc[i];
+            }
+            if constexpr (FUSED) {
+                // queued (at most a head and a tail row per slice)
+                if (tid == 0) {
+                    pend_r[n_pend] = r;
+                    pend_nseg[n_pend] = nseg;
+                }
+                ++n_pend;
+            }
+        }
+    }
+    if constexpr (!FUSED) break;
+    }   // slices
+    flush_pending();
+    if constexpr (FUSED) {
+        // the last CTA to finish re-arms the slice counter for the next launch
+        if (tid == 0 && n_slices != (int)gridDim.x) {
+            __threadfence();
+            if (atomicAdd(&row_done[B + 1], 1) == (int)gridDim.x - 1) {
+                row_done[B] = 0;
+                row_done[B + 1] = 0;
             }
         }
     }
@@ -566,7 +704,7 @@ static int plan_attention(mli_ctx* ctx, int B, int S, int d, bool fused, AttnPla
     if (nstage > kMaxStages) nstage = kMaxStages;
     p->nstage = nstage;
     p->smem = nstage * stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
-              2 * kConsumerWarps * G * sizeof(float) + 16 * sizeof(int) + 128;
+              2 * kConsumerWarps * G * sizeof(float) + kAttnCtrlInts * sizeof(int) + 128;
     int ch = ctx->attn_chunk_pages;
     if (ch <= 0) {
         // aim for a few items per persistent CTA without making items tiny
@@ -623,10 +761,10 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     rc = ws_get(ctx, WS_ATTN_META, attention_meta_bytes(B, p.max_items), &meta);
     if (rc) return rc;
     // partial slots: one per (row, chunk) item (legacy) or two per CTA (fused: slice head / tail)
-    const size_t n_part = std::max((size_t)p.max_items, (size_t)2 * p.grid);
+    const size_t n_part = std::max((size_t)p.max_items, (size_t)2 * 5 * p.grid);   // fused: <= 4 * grid + grid slices
     rc = ws_get(ctx, WS_ATTN_PART, sizeof(float) * (n_part * (d + 2) + 8), &part);
     if (rc) return rc;
-    rc = ws_get_zeroed(ctx, WS_ATTN_CNT, sizeof(int) * (size_t)B, &cnt);
+    rc = ws_get_zeroed(ctx, WS_ATTN_CNT, sizeof(int) * ((size_t)B + 2), &cnt);   // + slice / finished-CTA counters
     if (rc) return rc;
     int* row_first = reinterpret_cast<int*>(meta);
     int* item_row = row_first + B + 1;

@@ -22,6 +22,9 @@ def main():
     B, d, S, frac = (int(x) for x in sys.argv[1:5]) if len(sys.argv) >= 5 else (256, 1024, 128, 58)
     torch.cuda.set_device(0)
     ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
+    import os
+    if os.environ.get("ATTN_CTAS"):
+        ctx.set_option(mli.OPT_ATTN_CTAS_PER_SM, int(os.environ["ATTN_CTAS"]))
     rng = np.random.default_rng(0)
     L = rng.integers(1, S - 1, size=B).astype(np.int32)
     L[rng.random(B) > frac / 100.0] = 0          # ~58 % of rows active, as in the bench job
