@@ -89,10 +89,28 @@ static int latest_paged(mli_ctx* ctx, float** page_table, const int* lengths, co
     return launch_qkv_latest_paged_simt(ctx, page_table, lengths, wk, wq, wv, q_output, B, S, d);
 }
 
-static int logits(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V,
-                  int d) {
-    if (use_tc(ctx)) return launch_logits_tc(ctx, attn, emb, score, B, V, d);
-    return launch_logits_simt(ctx, attn, emb, score, B, V, d);
+// logits + decoder.  Tensor-core mode: split-K partial planes in a workspace, summed by the decoder
+// (which also writes them to emb_score when the caller wants the logits); exact mode: plain logits.
+static int logits_and_decode(mli_ctx* ctx, const float* attn, const float* emb, float* emb_score,
+                             const float* pos, float* const* page_table, int* lengths,
+                             int* decoder_result, int B, int V, int S, int d, int n_dec, int i_dec) {
+    int rc;
+    void* p;
+    if (use_tc(ctx)) {
+        if ((rc = ws_get(ctx, WS_LOGITS, sizeof(float) * (size_t)kMaxLogitSplit * B * V, &p))) return rc;
+        float* part = reinterpret_cast<float*>(p);
+        int n_split = 1;
+        if ((rc = launch_logits_tc(ctx, attn, emb, part, B, V, d, &n_split))) return rc;
+        return launch_paged_decoder(ctx, part, n_split, emb_score, decoder_result, lengths, page_table,
+                                    pos, emb, B, V, S, d, n_dec, i_dec);
+    }
+    if (!emb_score) {
+        if ((rc = ws_get(ctx, WS_LOGITS, sizeof(float) * (size_t)B * V, &p))) return rc;
+        emb_score = reinterpret_cast<float*>(p);
+    }
+    if ((rc = launch_logits_simt(ctx, attn, emb, emb_score, B, V, d))) return rc;
+    return launch_paged_decoder(ctx, emb_score, 1, nullptr, decoder_result, lengths, page_table, pos,
+                                emb, B, V, S, d, n_dec, i_dec);
 }
 
 }  // namespace mli
@@ -303,15 +321,9 @@ int mli_paged_decoder(mli_ctx* ctx, const float* batch_result, const float* emb_
     MLI_REQUIRE(n_vocab > 0 && n_decoder_results > 0 && i_decoder >= 0 &&
                     i_decoder < n_decoder_results,
                 "bad decoder dims");
-    if (!emb_score) {
-        void* p;
-        if ((rc = ws_get(ctx, WS_LOGITS, sizeof(float) * (size_t)n_batch * n_vocab, &p))) return rc;
-        emb_score = reinterpret_cast<float*>(p);
-    }
-    if ((rc = logits(ctx, batch_result, emb_table, emb_score, n_batch, n_vocab, emb_dim))) return rc;
-    return launch_paged_decoder(ctx, emb_score, decoder_result, lengths, page_table, pos_table,
-                                emb_table, n_batch, n_vocab, n_sequence, emb_dim, n_decoder_results,
-                                i_decoder);
+    return logits_and_decode(ctx, batch_result, emb_table, emb_score, pos_table, page_table, lengths,
+                             decoder_result, n_batch, n_vocab, n_sequence, emb_dim, n_decoder_results,
+                             i_decoder);
 }
 
 int mli_paged_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new_item_indices,
@@ -332,9 +344,6 @@ int mli_paged_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new
         if ((rc = ws_get(ctx, WS_ATTN_OUT, sizeof(float) * (size_t)n_batch * emb_dim, &p))) return rc;
         attention_result = reinterpret_cast<float*>(p);
     }
-    if ((rc = ws_get(ctx, WS_LOGITS, sizeof(float) * (size_t)n_batch * n_vocab, &p))) return rc;
-    float* score = reinterpret_cast<float*>(p);
-
     for (int round = 0; round < n_forward_rounds; ++round) {
         if (round == 0 && n_new_items > 0) {
             const int max_tiles = n_new_items * ceil_div(n_sequence, kTileM);
@@ -358,11 +367,9 @@ int mli_paged_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new
         if ((rc = launch_decode_attention_paged(ctx, q_output, page_table, lengths, attention_result,
                                                 nullptr, n_batch, n_sequence, emb_dim)))
             return rc;
-        if ((rc = logits(ctx, attention_result, emb_table, score, n_batch, n_vocab, emb_dim)))
-            return rc;
-        if ((rc = launch_paged_decoder(ctx, score, decoder_result, lengths, page_table, pos_table,
-                                       emb_table, n_batch, n_vocab, n_sequence, emb_dim,
-                                       n_forward_rounds, round)))
+        if ((rc = logits_and_decode(ctx, attention_result, emb_table, nullptr, pos_table, page_table,
+                                    lengths, decoder_result, n_batch, n_vocab, n_sequence, emb_dim,
+                                    n_forward_rounds, round)))
             return rc;
     }
     return MLI_OK;

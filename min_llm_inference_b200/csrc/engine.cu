@@ -487,8 +487,10 @@ struct mli_engine {
     int* stage_buf = nullptr;  // device staging for host prompts
     size_t stage_ints = 0;
     std::vector<void*> allocs;
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;   // one step (bounded runs)
     cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graphn_exec = nullptr;  // kStepsPerGraph steps (runs to completion)
+    cudaGraph_t graphn = nullptr;
     int n_req = 0;
     mli_engine_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -589,13 +591,16 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1) {
                                            nullptr, B, S, d);
         ctx->attn_ev_start = ctx->attn_ev_stop = nullptr;
         if (rc) return rc;
+        int n_split = 1;
         if (ctx->gemm_mode == 0 && ctx->tc_available)
-            rc = launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d, e->a.act_rows, e->a.counts);
+            rc = launch_logits_tc(ctx, e->attn_out, e->emb, e->score, B, V, d, &n_split, e->a.act_rows,
+                                  e->a.counts);
         else
             rc = launch_logits_simt(ctx, e->attn_out, e->emb, e->score, B, V, d);
         if (rc) return rc;
-        if ((rc = launch_paged_decoder(ctx, e->score, e->a.dec, e->a.lengths, e->a.page_table, e->pos,
-                                       e->emb, B, V, S, d, c.n_forward_rounds, round)))
+        if ((rc = launch_paged_decoder(ctx, e->score, n_split, nullptr, e->a.dec, e->a.lengths,
+                                       e->a.page_table, e->pos, e->emb, B, V, S, d, c.n_forward_rounds,
+                                       round)))
             return rc;
     }
     return 0;
@@ -603,14 +608,29 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1) {
 
 // one engine iteration: scheduler (the head of the step: plain launch, fully ordered after the
 // previous step), then the model
-int enqueue_step(mli_engine* e) {
-    e->a.trace = e->ctx->trace;
-    sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), e->ctx->stream>>>(e->a);
-    MLI_LAUNCH_CHECK();
+// chained = true: the scheduler itself is launched with programmatic dependent launch (it follows
+// the previous step's decoder inside one multi-step graph)
+int enqueue_step(mli_engine* e, bool chained = false) {
+    mli_ctx* ctx = e->ctx;
+    e->a.trace = ctx->trace;
+    if (chained && ctx->opt_pdl) {
+        ctx->use_pdl = true;
+        int rc = launch_kernel(ctx, sched_step_kernel, dim3(1), dim3(sched_threads(e->cfg.n_batch)),
+                               sched_smem_bytes(e->cfg.n_batch), e->a);
+        ctx->use_pdl = false;
+        if (rc) return rc;
+    } else {
+        sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), ctx->stream>>>(e->a);
+        MLI_LAUNCH_CHECK();
+    }
     return enqueue_model(e, nullptr, nullptr);
 }
 
 void drop_graph(mli_engine* e) {
+    if (e->graphn_exec) cudaGraphExecDestroy(e->graphn_exec);
+    if (e->graphn) cudaGraphDestroy(e->graphn);
+    e->graphn_exec = nullptr;
+    e->graphn = nullptr;
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->graph) cudaGraphDestroy(e->graph);
     e->graph_exec = nullptr;
@@ -673,7 +693,7 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     A(dev_alloc(e, &a.counts, 4));
     A(dev_alloc(e, &e->q_out, (size_t)B * d));
     A(dev_alloc(e, &e->attn_out, (size_t)B * d));
-    A(dev_alloc(e, &e->score, (size_t)B * V));
+    A(dev_alloc(e, &e->score, (size_t)kMaxLogitSplit * B * V));   // split-K partial logits
     e->max_tiles = B * ceil_div(S, kTileM);
     A(dev_alloc(e, &e->tiles, e->max_tiles));
     A(dev_alloc(e, &e->n_tiles, 4));
@@ -844,30 +864,40 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             if (*reinterpret_cast<volatile int*>(e->done_host)) finished = true;
         }
     } else {
-        if (!e->graph_exec) {
+        // Runs to completion replay a graph of kStepsPerGraph steps (every scheduler after the
+        // first is chained to the previous decoder with programmatic dependent launch; steps past
+        // the end of the job find an empty engine and cost a few microseconds); bounded runs replay
+        // a one-step graph.
+        constexpr int kStepsPerGraph = 4;
+        const int per = (max_steps > 0) ? 1 : kStepsPerGraph;
+        cudaGraphExec_t& gexec = (per == 1) ? e->graph_exec : e->graphn_exec;
+        cudaGraph_t& g = (per == 1) ? e->graph : e->graphn;
+        if (!gexec) {
             MLI_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const long long l0 = mli_kernel_launch_count();
-            rc = enqueue_step(e);
-            e->launches_per_step = (int)(mli_kernel_launch_count() - l0);
-            count_launch(-e->launches_per_step);   // captured, not launched
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e->graph);
+            rc = 0;
+            for (int k = 0; k < per && !rc; ++k) rc = enqueue_step(e, k > 0);
+            e->launches_per_step = (int)(mli_kernel_launch_count() - l0) / per;
+            count_launch(-e->launches_per_step * per);   // captured, not launched
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
             if (rc || ce != cudaSuccess) {
-                if (e->graph) cudaGraphDestroy(e->graph);
-                e->graph = nullptr;
+                if (g) cudaGraphDestroy(g);
+                g = nullptr;
                 cudaGetLastError();
                 return rc ? rc : cuda_fail(ce, __FILE__, __LINE__);
             }
-            MLI_CUDA(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+            MLI_CUDA(cudaGraphInstantiate(&gexec, g, 0));
             ctx->ws_frozen = true;
         }
-        constexpr int kAhead = 4;
-        for (;; ++it) {
+        const int kAhead = (per == 1) ? 4 : 2;   // graphs in flight before the host looks at `done`
+        for (;; it += per) {
             if (max_steps > 0 && it >= max_steps) break;
-            if (it >= kAhead) MLI_CUDA(cudaEventSynchronize(e->ring_ev[it % kAhead]));
+            const int slot = (int)((it / per) % kAhead);
+            if (it / per >= kAhead) MLI_CUDA(cudaEventSynchronize(e->ring_ev[slot]));
             if (*reinterpret_cast<volatile int*>(e->done_host)) break;
-            MLI_CUDA(cudaGraphLaunch(e->graph_exec, ctx->stream));
-            count_launch(e->launches_per_step);
-            MLI_CUDA(cudaEventRecord(e->ring_ev[it % kAhead], ctx->stream));
+            MLI_CUDA(cudaGraphLaunch(gexec, ctx->stream));
+            count_launch(e->launches_per_step * per);
+            MLI_CUDA(cudaEventRecord(e->ring_ev[slot], ctx->stream));
         }
     }
     MLI_CUDA(cudaEventRecord(e->ev_end, ctx->stream));

@@ -148,6 +148,8 @@ struct TcArgs {
     const int* counts;     // [0] = active rows, [1] = granules (device-side)
     const TileDesc* gran;  // STEP: 16-position prefill granules of the new rows
     int use_gran;
+    int defer;             // LOGITS: every split rank stores its partial plane (no cross-CTA reduce)
+    size_t defer_stride;   // floats between partial planes
     int V, W, B;
     int bn;                // activation rows per tile: multiple of 16, <= 256 (the UMMA N)
     int n_stages;          // smem pipeline depth
@@ -320,7 +322,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < nst; ++s) {
             mbar_init(&full_w[s], 1);
-            mbar_init(&full_x[s], kTcConvThreads);
+            mbar_init(&full_x[s], kTcConvThreads / 32);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
@@ -333,17 +335,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const uint32_t tmem_acc = *tmem_ptr_smem;
 
     TC_STAMP(1);
+    const int num_kb = args.K / kBK;
+    const int kb_per = num_kb / split;          // host guarantees divisibility
+    const int kb0 = krank * kb_per, kb1 = kb0 + kb_per;
+    const int kb_per_acc = (kb_per + args.n_acc - 1) / args.n_acc;
+    // The weights are static: the producer starts filling the pipeline with weight tiles right away,
+    // before this kernel is allowed to look at anything its predecessor wrote.
+    const int n_pre = min(nst, kb_per);
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < n_pre; ++i) {
+            unsigned char* st = base + (size_t)i * stage_bytes;
+            mbar_expect_tx(&full_w[i], 2 * kWBytes);
+            tma_load_2d(st, &map_a_hi, (kb0 + i) * kBK, m0, &full_w[i]);
+            tma_load_2d(st + kWBytes, &map_a_lo, (kb0 + i) * kBK, m0, &full_w[i]);
+        }
+    }
     // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
     griddep_wait();
     griddep_launch_dependents();
     trace_stamp(args.trace, args.trace_slot);
 
     const int n_valid = tc_n_valid(args);
-
-    const int num_kb = args.K / kBK;
-    const int kb_per = num_kb / split;          // host guarantees divisibility
-    const int kb0 = krank * kb_per, kb1 = kb0 + kb_per;
-    const int kb_per_acc = (kb_per + args.n_acc - 1) / args.n_acc;
 
     uint32_t it = 0;        // pipeline counter (runs on across tiles; identical in every role)
     uint32_t tile_iter = 0;
@@ -363,6 +375,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (lane == 0) {
                 uint32_t i = it;
                 for (int kb = kb0; kb < kb1; ++kb, ++i) {
+                    if (tile_iter == 0 && kb - kb0 < n_pre) continue;   // issued before the wait
                     const int s = i % nst;
                     mbar_wait(&empty_bar[s], ((i / nst) & 1) ^ 1);
                     unsigned char* st = base + (size_t)s * stage_bytes;
@@ -443,8 +456,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         *reinterpret_cast<float4*>(xl + off) = l;
                     }
                 }
+                // every thread orders its own stores for the async proxy; one arrival per warp
                 fence_proxy_async_smem();
-                mbar_arrive(&full_x[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_x[s]);
             };
             load_set(ra, kb0);
             if (kb0 + 1 < kb1) load_set(rb, kb0 + 1);
@@ -475,40 +490,49 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += u[j];
                 }
-                if (split == 1) {
+                // transpose through shared memory: [row][feature] so that rows leave as 512-byte runs
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float* p = (c0 + j < n_eff) ? dst_tab[c0 + j] : nullptr;
-                        if (p != nullptr) p[q * 32 + lane] = v[j];   // 32 lanes -> 128 contiguous bytes
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < n_eff) part[(size_t)(c0 + j) * kBM + q * 32 + lane] = v[j];
-                }
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < n_eff) part[(size_t)(c0 + j) * kBM + q * 32 + lane] = v[j];
             }
             tc_fence_before();
         }
         // ---- split-K exchange: rank z sums rows z, z + split, ... of all partial tiles ----
         cluster_sync_all();
         TC_STAMP(5);
-        if (split > 1) {
+        {
+            // rank z stores rows z, z + split, ... summed over all ranks' partial tiles (fixed order);
+            // with a deferred reduce (or no split) every CTA stores all rows of its own tile
+            const bool own_only = (split == 1) || args.defer;
+            const int row_step = own_only ? 1 : split;
+            const int row_first = own_only ? 0 : krank;
+            const int n_src = own_only ? 1 : split;
+            const size_t plane = args.defer ? (size_t)krank * args.defer_stride : 0;
             const int f4 = tid & 31;
-            uint32_t raddr[8];
+            if (own_only) {
+                for (int n = tid >> 5; n < n_eff; n += kTcThreadsV2 / 32) {
+                    float* p = dst_tab[n];
+                    if (p == nullptr) continue;
+                    reinterpret_cast<float4*>(p + plane)[f4] =
+                        *reinterpret_cast<const float4*>(part + (size_t)n * kBM + f4 * 4);
+                }
+            } else {
+                uint32_t raddr[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) raddr[r] = dsmem_addr(part + f4 * 4, (uint32_t)(r < split ? r : 0));
-            for (int n = krank + split * (tid >> 5); n < n_eff; n += split * (kTcThreadsV2 / 32)) {
-                float* p = dst_tab[n];
-                if (p == nullptr) continue;
-                float4 t[8];
+                for (int r = 0; r < 8; ++r) raddr[r] = dsmem_addr(part + f4 * 4, (uint32_t)(r < split ? r : 0));
+                for (int n = row_first + row_step * (tid >> 5); n < n_eff; n += row_step * (kTcThreadsV2 / 32)) {
+                    float* p = dst_tab[n];
+                    if (p == nullptr) continue;
+                    float4 t[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (r < split) t[r] = ld_dsmem_f4(raddr[r] + (uint32_t)n * (kBM * 4));
-                float4 sum = t[0];
+                    for (int r = 0; r < 8; ++r)
+                        if (r < n_src) t[r] = ld_dsmem_f4(raddr[r] + (uint32_t)n * (kBM * 4));
+                    float4 sum = t[0];
 #pragma unroll
-                for (int r = 1; r < 8; ++r)
-                    if (r < split) { sum.x += t[r].x; sum.y += t[r].y; sum.z += t[r].z; sum.w += t[r].w; }
-                reinterpret_cast<float4*>(p)[f4] = sum;
+                    for (int r = 1; r < 8; ++r)
+                        if (r < n_src) { sum.x += t[r].x; sum.y += t[r].y; sum.z += t[r].z; sum.w += t[r].w; }
+                    reinterpret_cast<float4*>(p)[f4] = sum;
+                }
             }
         }
         TC_STAMP(6);
@@ -518,6 +542,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         cluster_sync_all();   // partial tiles and row tables may be reused
         tc_fence_after();
         it += (uint32_t)kb_per;
+    }
+    if (tile_iter == 0 && warp == 0 && lane == 0) {
+        // nothing to do after all: the prefetched weight tiles must land before the CTA may exit
+        for (int i = 0; i < n_pre; ++i) mbar_wait(&full_w[i], 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -690,7 +718,8 @@ size_t tc_smem_bytes(int n_stages, int bn) {
 // (one SM ingests ~60-100 GB/s), so the activation tile is made as wide as the UMMA allows
 // (weights are then read once per 256 rows) and K is split across a cluster until the launch
 // covers the GPU in a single wave.
-int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int expect_rows) {
+int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int expect_rows,
+             int* split_out = nullptr) {
     const long long rows = args.n_rows;
     if (rows <= 0) return 0;
     // expect_rows: rows the launch will typically see (prefill: device-side count, usually small)
@@ -703,7 +732,8 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     const int n_tiles_all = (int)((rows + bn - 1) / bn);
     const int num_kb = args.K / kBK;
     int split = 1;
-    for (int s = 8; s >= 2; s >>= 1) {
+    // a cluster holds at most 8 CTAs; deferred-reduce launches have independent ranks
+    for (int s = args.defer ? kMaxLogitSplit : 8; s >= 2; s >>= 1) {
         if (num_kb % s == 0 && num_kb / s >= 2 && (long long)m_tiles * n_tiles_plan * s <= ctx->num_sms) {
             split = s;
             break;
@@ -748,8 +778,9 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     attrs[na].id = cudaLaunchAttributeClusterDimension;
     attrs[na].val.clusterDim.x = 1;
     attrs[na].val.clusterDim.y = 1;
-    attrs[na].val.clusterDim.z = (unsigned)split;
+    attrs[na].val.clusterDim.z = args.defer ? 1u : (unsigned)split;   // deferred: ranks are independent
     ++na;
+    if (split_out) *split_out = split;
     if (ctx->use_pdl) {
         attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[na].val.programmaticStreamSerializationAllowed = 1;
@@ -862,7 +893,8 @@ int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* length
 }
 
 int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V, int d,
-                     const int* act_rows, const int* counts) {
+                     int* n_split, const int* act_rows, const int* counts) {
+    *n_split = 1;
     if (!shapes_ok(d, V)) return launch_logits_simt(ctx, attn, emb, score, B, V, d);
     OperandEntry* w = nullptr;
     int rc = get_operand(ctx, emb, nullptr, nullptr, V, d, &w);
@@ -870,7 +902,8 @@ int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* s
     TcArgs a{};
     a.mode = TC_LOGITS; a.K = d; a.d = d; a.n_rows = B; a.score = score; a.V = V; a.B = B;
     a.dense_src = attn; a.act = act_rows; a.counts = (act_rows != nullptr) ? counts : nullptr;
-    return run_gemm(ctx, w, a, V / kBM, 0);
+    a.defer = 1; a.defer_stride = (size_t)B * V;
+    return run_gemm(ctx, w, a, V / kBM, 0, n_split);
 }
 
 }  // namespace mli

@@ -59,9 +59,13 @@ int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const Til
 int launch_qkv_latest_paged_tc(mli_ctx* ctx, float* const* page_table, const int* lengths,
                                const float* wk, const float* wq, const float* wv, float* q_output,
                                int B, int S, int d);
-// act_rows / counts (optional, device): only rows act_rows[0..counts[0]) are computed
-int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V,
-                     int d, const int* act_rows = nullptr, const int* counts = nullptr);
+// Split-K partial logits: part[z][B][V] for z < *n_split (kMaxLogitSplit * B * V floats); the
+// decoder adds the partials in rank order while it scans for the argmax, so the GEMM needs no
+// cross-CTA reduction.  act_rows / counts (optional, device): only rows act_rows[0..counts[0]) are
+// computed.
+constexpr int kMaxLogitSplit = 16;
+int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* part, int B, int V,
+                     int d, int* n_split, const int* act_rows = nullptr, const int* counts = nullptr);
 // the engine's merged projection: latest-token K,q,V of the active rows AND prefill K,V of the new
 // rows' earlier positions in ONE launch.  act_rows[0..counts[0]) = active rows, gran[0..counts[1]) =
 // 16-position granules of the new rows (ignored when use_gran == 0, i.e. forward rounds > 0).
@@ -80,7 +84,10 @@ int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_
 double attention_algorithmic_bytes(const int* lengths_host, int B, int d);
 
 // ---- decoder (src/kernels/decoder.cu:25-91, :128-205) -------------------------------------------
-int launch_paged_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
+// score = n_split partial logit planes [n_split][B][V] (1 = plain logits); score_out (optional)
+// receives the summed logits
+int launch_paged_decoder(mli_ctx* ctx, const float* score, int n_split, float* score_out,
+                         int* decoder_result, int* lengths,
                          float* const* page_table, const float* pos, const float* emb, int B, int V,
                          int S, int d, int n_dec, int i_dec);
 int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,

@@ -157,7 +157,8 @@ int launch_dense_encoder(mli_ctx* ctx, const float* emb, const float* pos, const
 // ---------------------------------------------------------------------------------------------
 template <bool PAGED>
 __global__ void __launch_bounds__(256)
-decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result,
+decoder_kernel(const float* __restrict__ score, int n_split, size_t split_stride,
+               float* __restrict__ score_out, int* __restrict__ decoder_result,
                int* __restrict__ lengths, float* const* __restrict__ page_table,
                float* __restrict__ inp_embedding, const float* __restrict__ pos,
                const float* __restrict__ emb, int V, int S, int d, int n_dec, int i_dec,
@@ -177,9 +178,35 @@ decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result
     const float* s = score + (size_t)r * V;
     float lm = -FLT_MAX;
     int li = -1;
-    for (int i = tid; i < V; i += 256) {
-        const float v = s[i];
-        if (v > lm) { lm = v; li = i; }
+    // thread t scans t, t+256, ... in ascending order (the reference's order, so the first strict
+    // maximum wins); four indices are handled per round so that the loads of all partial planes
+    // are in flight together, then the planes are added in rank order
+    for (int i0 = tid; i0 < V; i0 += 1024) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (i0 + 256 * u < V) ? s[i0 + 256 * u] : 0.f;
+        for (int z0 = 1; z0 < n_split; z0 += 8) {
+            float t[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    t[u][w] = (z0 + w < n_split && i0 + 256 * u < V)
+                                  ? s[(size_t)(z0 + w) * split_stride + i0 + 256 * u] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    if (z0 + w < n_split) v[u] += t[u][w];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 256 * u;
+            if (i < V) {
+                if (score_out != nullptr) score_out[(size_t)r * V + i] = v[u];
+                if (v[u] > lm) { lm = v[u]; li = i; }
+            }
+        }
     }
     mv[tid] = lm;
     mi[tid] = li;
@@ -217,17 +244,20 @@ decoder_kernel(const float* __restrict__ score, int* __restrict__ decoder_result
     }
 }
 
-int launch_paged_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
+int launch_paged_decoder(mli_ctx* ctx, const float* score, int n_split, float* score_out,
+                         int* decoder_result, int* lengths,
                          float* const* page_table, const float* pos, const float* emb, int B, int V,
                          int S, int d, int n_dec, int i_dec) {
-    return launch_kernel(ctx, decoder_kernel<true>, dim3(B), dim3(256), 0, score, decoder_result, lengths,
+    return launch_kernel(ctx, decoder_kernel<true>, dim3(B), dim3(256), 0, score, n_split, (size_t)B * V,
+                         score_out, decoder_result, lengths,
                          page_table, static_cast<float*>(nullptr), pos, emb, V, S, d, n_dec, i_dec, ctx->trace);
 }
 
 int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
                          float* inp_embedding, const float* pos, const float* emb, int B, int V, int S,
                          int d) {
-    return launch_kernel(ctx, decoder_kernel<false>, dim3(B), dim3(256), 0, score, decoder_result, lengths,
+    return launch_kernel(ctx, decoder_kernel<false>, dim3(B), dim3(256), 0, score, 1, (size_t)0,
+                         static_cast<float*>(nullptr), decoder_result, lengths,
                          static_cast<float* const*>(nullptr), inp_embedding, pos, emb, V, S, d, 1, 0,
                          static_cast<unsigned long long*>(nullptr));
 }
