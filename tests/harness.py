@@ -215,3 +215,46 @@ def run_oracle_engine(kind, cfg: dict, w, offs, toks, fix=0, max_steps=0, thread
             p(offs), p(toks), p(ids), p(fo), p(ft), C.byref(st))
     res = {int(ids[i]): ft[fo[i]:fo[i + 1]].copy() for i in range(st.n_finished)}
     return rc, res, ids[:st.n_finished].copy(), st
+
+
+def top2_margin_f64(w, tokens, t):
+    """float64 replay of ONE request up to position t (tokens[:t] are given): returns
+    (best token, runner-up token, (best - runner-up) / max|logit|).  Used to decide whether a token
+    that differs between two fp32 evaluation orders sits on a numerical tie (mismatches are
+    classified by the top-2 margin of the logits)."""
+    E, P = w["emb"].astype(np.float64), w["pos"].astype(np.float64)
+    d = E.shape[1]
+    x = E[np.asarray(tokens[:t])] + P[:t]
+    K, V = x @ w["wk"].astype(np.float64), x @ w["wv"].astype(np.float64)
+    q = x[-1] @ w["wq"].astype(np.float64)
+    s = K @ q / np.sqrt(np.float64(d))
+    p = np.exp(s - s.max())
+    p /= p.sum()
+    logits = (p @ V) @ E.T
+    order = np.argsort(-logits)
+    scale = float(np.max(np.abs(logits)))
+    return int(order[0]), int(order[1]), float(logits[order[0]] - logits[order[1]]) / max(scale, 1e-300)
+
+
+def classify_token_mismatches(w, mine, want, tie_rel=2e-5):
+    """requests whose token lists differ -> list of (request, position, margin).  A mismatch is a
+    numerical TIE when, at the first differing position, the two tokens are the float64 top-2 and
+    their logits differ by less than tie_rel of the largest |logit| (the 3xTF32 / fp32 re-association
+    noise level); anything else is a real error (margin = None)."""
+    ties, errors = [], []
+    for i in sorted(want):
+        a, b = np.asarray(mine[i]), np.asarray(want[i])
+        if a.shape == b.shape and np.array_equal(a, b):
+            continue
+        n = min(len(a), len(b))
+        diff = np.flatnonzero(a[:n] != b[:n])
+        t = int(diff[0]) if len(diff) else n
+        if t >= n:
+            errors.append((i, t, None))
+            continue
+        best, second, margin = top2_margin_f64(w, b, t)
+        if {int(a[t]), int(b[t])} == {best, second} and margin < tie_rel:
+            ties.append((i, t, margin))
+        else:
+            errors.append((i, t, margin))
+    return ties, errors
