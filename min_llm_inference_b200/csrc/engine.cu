@@ -414,6 +414,10 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         v->iter = sv.iter + 1;
         a.counts[0] = n_act;
         a.counts[1] = min(n_gran, a.max_gran);
+        if (a.trace != nullptr && a.trace[0] >= 1 && a.trace[0] - 1 < a.trace[1]) {
+            a.trace[8 + 8 * (a.trace[0] - 1) + 6] = (unsigned long long)n_act;    // for tools/step_timeline.py
+            a.trace[8 + 8 * (a.trace[0] - 1) + 7] = (unsigned long long)n_gran;
+        }
         // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
         if (n_used + qc == 0) {
             v->done = 1;

@@ -358,17 +358,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int n_valid = tc_n_valid(args);
 
     uint32_t it = 0;        // pipeline counter (runs on across tiles; identical in every role)
-    uint32_t tile_iter = 0;
-    for (int nt = blockIdx.y; nt * bn < n_valid; nt += gridDim.y, ++tile_iter) {
+    uint32_t tile_iter = 0;   // tiles this CTA really processed
+    for (int nt = blockIdx.y; nt * bn < n_valid; nt += gridDim.y) {
         const int n0 = nt * bn;
         const int n_eff = min(bn, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
         // ---- row tables of the tile ----
+        bool live = false;
         if (tid < bn) {
             const RowIO io = row_io(args, n0 + tid, n_valid, mat, f0);
             src_tab[tid] = io.src;
             dst_tab[tid] = io.dst;
+            live = io.dst != nullptr;
         }
-        __syncthreads();
+        // A tile none of whose rows wants this CTA's features (q features over a tile of prefill
+        // positions) is skipped.  The decision depends only on (feature tile, activation tile), so
+        // it is the same in every CTA of the cluster.
+        if (!__syncthreads_or(live)) continue;
 
         if (warp == 0) {
             // ===================== TMA producer (weights) =====================
@@ -542,6 +547,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         cluster_sync_all();   // partial tiles and row tables may be reused
         tc_fence_after();
         it += (uint32_t)kb_per;
+        ++tile_iter;
     }
     if (tile_iter == 0 && warp == 0 && lane == 0) {
         // nothing to do after all: the prefetched weight tiles must land before the CTA may exit
@@ -742,6 +748,7 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     int ny = n_tiles_all;
     const int cap = std::max(1, ctx->num_sms / (m_tiles * split));
     if (ny > cap) ny = std::max(cap, std::min(n_tiles_plan, n_tiles_all));
+
     args.bn = bn;
     args.acc_stride = (bn + 31) / 32 * 32;
     const int k_per_cta = args.K / split;

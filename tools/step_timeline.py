@@ -56,7 +56,9 @@ def main():
     torch.cuda.synchronize()
     t = trace.cpu().numpy()
     n = int(min(t[0], cap))
-    tl = t[8:8 + 8 * n].reshape(n, 8)[:, :6].astype(np.float64)
+    full = t[8:8 + 8 * n].reshape(n, 8)
+    tl = full[:, :6].astype(np.float64)
+    n_act, n_gran = full[:, 6].astype(np.int64), full[:, 7].astype(np.int64)
     real = int(st.steps)
     # duration of kernel k of step i = stamp of the next kernel - its own stamp
     nxt = np.concatenate([tl[:, 1:], np.vstack([tl[1:, :1], [[np.nan]]])], axis=1)
@@ -75,6 +77,22 @@ def main():
         lines.append(f"| {name} | {col.mean():.1f} | {np.median(col):.1f} | {np.percentile(col, 90):.1f} | "
                      f"{100 * col.mean() / tot:.1f}% |")
     lines.append(f"\nSum of means {tot:.1f} us per iteration.")
+    # the merged GEMM against the rows it saw (active rows padded to 16 + 16 per prefill granule)
+    rows = ((n_act + 15) // 16 * 16 + 16 * n_gran)[:real - 1]
+    g = dur[:, 2]
+    lines += ["", "QKV+prefill GEMM by activation rows of the step (256 rows = one tile):", "",
+              "| rows | steps | mean us | mean active rows | mean granules |", "|---|---:|---:|---:|---:|"]
+    for lo, hi in ((0, 128), (129, 256), (257, 512), (513, 1 << 30)):
+        m = (rows >= lo) & (rows <= hi) & ~np.isnan(g)
+        if m.any():
+            lines.append(f"| {lo}-{hi if hi < 1 << 30 else 'inf'} | {int(m.sum())} | {g[m].mean():.1f} | "
+                         f"{n_act[:real - 1][m].mean():.0f} | {n_gran[:real - 1][m].mean():.1f} |")
+    e = dur[:, 1]
+    for has in (False, True):
+        m = ((n_gran[:real - 1] > 0) == has) & ~np.isnan(e)
+        if m.any():
+            lines.append(f"\nencoder, steps {'with' if has else 'without'} new rows: {int(m.sum())} steps, "
+                         f"mean {e[m].mean():.1f} us")
     text = "\n".join(lines)
     print(text)
     if args.out:
