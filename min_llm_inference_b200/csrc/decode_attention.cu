@@ -98,7 +98,7 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // counter in global memory, self-resetting).  B <= kMaxFusedRows.
 // FUSED = false: (row, chunk) items from attn_prep_kernel, merge by attn_combine_kernel -- used when
 // the [B,S] probabilities are requested or B is too large for the shared-memory prefix.
-constexpr int kMaxFusedRows = 4096;
+constexpr int kMaxFusedRows = 8192;
 constexpr int kMaxPend = 32;
 constexpr int kMinDynFair = 256;   // positions per CTA below which all slices are static
 constexpr int kAttnCtrlInts = 16 + kMaxStages + 3 * kMaxPend;

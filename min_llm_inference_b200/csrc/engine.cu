@@ -91,8 +91,12 @@ __device__ int block_scan_excl(int v, int* total, int* s_warp) {
     return res;
 }
 
-// shared-memory footprint of the scheduler: five int arrays and one pointer array of B entries
-size_t sched_smem_bytes(int B) { return (size_t)B * (5 * sizeof(int) + sizeof(float*)) + 64; }
+// shared-memory footprint of the scheduler: six int arrays of B entries and the free-page window
+constexpr int kMaxFreeWindow = 2048;   // pages one growth phase can take from shared memory
+__host__ __device__ inline int sched_window(int B) { return B < kMaxFreeWindow ? B : kMaxFreeWindow; }
+size_t sched_smem_bytes(int B) {
+    return (size_t)B * (6 * sizeof(int)) + (size_t)sched_window(B) * sizeof(float*) + 64;
+}
 
 // One CTA advances the whole continuous-batching state by one iteration.  Per-row state (request
 // of the row, pages of the row, the used-row list) is mirrored in shared memory for the duration of
@@ -103,21 +107,24 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     extern __shared__ __align__(16) unsigned char sched_smem[];
     __shared__ int s_warp[32];
     __shared__ int s_carry[4];
-    __shared__ SchedVars sv;
+    __shared__ long long s_pre;
     const int tid = threadIdx.x, T = blockDim.x;
     const int B = a.B, S = a.S, W = a.W, R = a.R;
-    float** fq = reinterpret_cast<float**>(sched_smem);          // [B] window of the free ring
-    int* s_req = reinterpret_cast<int*>(fq + B);                  // [B] row -> request (-1 = none)
+    const int n_fq = sched_window(B);
+    float** fq = reinterpret_cast<float**>(sched_smem);          // [n_fq] window of the free ring
+    int* s_req = reinterpret_cast<int*>(fq + n_fq);               // [B] row -> request (-1 = none)
     int* s_np = s_req + B;                                        // [B] pages of the row
     int* s_used = s_np + B;                                       // [B] used-row list
-    int* s_flag = s_used + B;                                     // [B] bit0 finished, bit1 unoccupied; later: occupied
+    int* s_flag = s_used + B;                                     // [B] bit0 finished, bit1 unoccupied, bits 2.. token count; later: occupied
     int* s_list = s_flag + B;                                     // [B] need list / free rows
+    int* s_len = s_list + B;                                      // [B] device lengths as the model kernels will see them
     griddep_wait();
     griddep_launch_dependents();
     trace_stamp(a.trace, 0);
 
-    if (tid == 0) sv = *a.v;
-    __syncthreads();
+    // every thread reads the counters itself (one broadcast line) together with its rows' state:
+    // one global round trip, no shared-memory hand-off
+    SchedVars sv = *a.v;
     if (sv.done) {
         if (tid == 0) {
             a.v->n_new = 0;
@@ -130,6 +137,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     for (int r = tid; r < B; r += T) {
         s_req[r] = a.row_req[r];
         s_np[r] = a.npages[r];
+        s_len[r] = a.lengths[r];
+        s_flag[r] = 0;
     }
     for (int i = tid; i < sv.n_used; i += T) s_used[i] = a.used[i];
     __syncthreads();
@@ -159,8 +168,11 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 }
                 if (finished || empty) break;
             }
-            if (id >= 0) a.req_cnt[id] = (finished && c > S) ? S : c;
-            s_flag[r] = (finished ? 1 : 0) | ((finished || empty) ? 2 : 0);
+            if (id >= 0) {
+                c = (finished && c > S) ? S : c;
+                a.req_cnt[id] = c;
+            }
+            s_flag[r] = (finished ? 1 : 0) | ((finished || empty) ? 2 : 0) | (c << 2);
         }
         if (local_gen) atomicAdd(reinterpret_cast<unsigned long long*>(&a.v->generated),
                                  (unsigned long long)local_gen);
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 int need = 0;
                 if (i < n_used) {
                     const int row = s_used[i];
-                    need = (a.req_cnt[s_req[row]] + R > s_np[row] * kPage) ? 1 : 0;
+                    need = ((s_flag[row] >> 2) + R > s_np[row] * kPage) ? 1 : 0;   // count from phase 1
                 }
                 int tot;
                 const int pos = block_scan_excl(need, &tot, s_warp);
@@ -229,8 +241,9 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 m += tot;
             }
             // window of the free ring the growth loop may consume: entry j = ring[fh + j]
-            const int n_win = min(F, m);
-            for (int j = tid; j < n_win; j += T) fq[j] = a.free_ring[(fh + j) % nb];
+            const int fh0 = fh;   // entry j of the window is ring[fh0 + j]
+            const int n_win = min(min(F, m), n_fq);
+            for (int j = tid; j < n_win; j += T) fq[j] = a.free_ring[(fh0 + j) % nb];
             __syncthreads();
             if (tid == 0) {
                 int n = n_used, taken = 0;   // taken = window entries consumed so far
@@ -238,14 +251,13 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 auto preempt = [&](int row) {
                     // move_to_new: front of the queue, keeping generated tokens (item_storage.cpp:75-79)
                     qh = (qh - 1 + q_cap) % q_cap;
-                    a.queue[qh] = s_req[row];
-                    ++qc;
+                    a.queue[qh] = s_req[row];   // (the queue count is adjusted by every thread below)
                     s_req[row] = -1;
                     const int np = s_np[row];
                     for (int t = 0; t < np; ++t) {
                         float* pg = a.page_table[(size_t)row * W + t];
                         a.free_ring[(fh + F + t) % nb] = pg;
-                        if (taken + F + t < B) fq[taken + F + t] = pg;   // only reachable when F <= m
+                        if (taken + F + t < n_fq) fq[taken + F + t] = pg;   // only reachable when F <= m
                     }
                     F += np;
                     s_np[row] = 0;
@@ -260,7 +272,11 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                             // allocate_memory_block (:196-203): new page at table index size-1
                             const int np = s_np[row];
                             if (np < W) {
-                                a.page_table[(size_t)row * W + np] = fq[taken];
+                                // beyond the window (more than kMaxFreeWindow growths in one step) the
+                                // page comes from the ring itself: everything written to it so far
+                                // was written by this thread
+                                a.page_table[(size_t)row * W + np] =
+                                    (taken < n_fq) ? fq[taken] : a.free_ring[(fh0 + taken) % nb];
                                 ++taken;
                                 fh = (fh + 1) % nb;
                                 --F;
@@ -281,15 +297,15 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 s_carry[1] = F;
                 s_carry[2] = fh;
                 s_carry[3] = qh;
-                sv.q_count = qc;
-                sv.preemptions += pre;
+                s_pre = pre;
             }
             __syncthreads();
+            qc += n_used - s_carry[0];   // every row dropped from the used list went to the queue
             n_used = s_carry[0];
             F = s_carry[1];
             fh = s_carry[2];
             qh = s_carry[3];
-            qc = sv.q_count;
+            sv.preemptions += s_pre;
             __syncthreads();
         }
     }
@@ -335,6 +351,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 for (int t = 0; t < np; ++t)
                     a.page_table[(size_t)row * W + t] = a.free_ring[(fh + before + t) % nb];
                 s_np[row] = np;
+                s_len[row] = len;
                 a.lengths[row] = len;
                 a.len_shadow[row] = len;
                 s_req[row] = id;
@@ -350,13 +367,18 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         // unoccupied rows that got nothing: length 0 (:109-112)
         for (int j = k_adm + tid; j < n_free_rows; j += T) {
             const int row = s_list[j];
+            s_len[row] = 0;
             a.lengths[row] = 0;
             a.len_shadow[row] = 0;
         }
         __syncthreads();
         // quirk Q1 (:113-118): any unoccupied row => the whole stale host array is copied back
         if (a.compat && n_free_rows > 0)
-            for (int r = tid; r < B; r += T) a.lengths[r] = a.len_shadow[r];
+            for (int r = tid; r < B; r += T) {
+                const int l0 = a.len_shadow[r];
+                s_len[r] = l0;
+                a.lengths[r] = l0;
+            }
         fh = (fh + pages_taken) % nb;
         F -= pages_taken;
         qh = (qh + k_adm) % q_cap;
@@ -376,7 +398,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int n_act = 0;
     for (int base = 0; base < B; base += T) {
         const int r = base + tid;
-        const int on = (r < B && a.lengths[r] > 0) ? 1 : 0;
+        const int on = (r < B && s_len[r] > 0) ? 1 : 0;
         int tot;
         const int pos = block_scan_excl(on, &tot, s_warp);
         if (on) a.act_rows[n_act + pos] = r;
@@ -387,8 +409,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         const int j = base + tid;
         int row = -1, n = 0;
         if (j < k_adm) {
-            row = a.new_idx[j];
-            n = (a.lengths[row] + kGran - 1) / kGran;
+            row = s_list[j];   // free row j took queue item j
+            n = (s_len[row] + kGran - 1) / kGran;
         }
         int tot;
         const int pos = block_scan_excl(n, &tot, s_warp);
@@ -655,8 +677,8 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
                 "bad engine dims");
     MLI_REQUIRE(cfg->n_forward_rounds >= 1 && cfg->n_forward_rounds <= kPage,
                 "n_forward_rounds must be 1..16");
-    MLI_REQUIRE(sched_smem_bytes(cfg->n_batch) <= 200 * 1024,
-                "n_batch too large for the device scheduler's shared-memory mirrors (max ~7000 rows per GPU)");
+    MLI_REQUIRE(sched_smem_bytes(cfg->n_batch) <= 220 * 1024,
+                "n_batch too large for the device scheduler's shared-memory mirrors (max ~10000 rows per GPU)");
     {
         static size_t configured = 48 * 1024;
         const size_t need = sched_smem_bytes(cfg->n_batch);

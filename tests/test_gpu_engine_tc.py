@@ -47,6 +47,9 @@ CASES = [
     dict(B=24, S=128, d=256, V=1024, n_blocks=120, n_req=60, lo=1, hi=48, R=3),
     # emb_dim the tensor-core kernels do not cover: the engine must route to the SIMT kernels
     dict(B=12, S=64, d=96, V=1000, n_blocks=48, n_req=30, lo=1, hi=30, R=1),
+    # BASELINE configs[4] at one GPU: 8192 rows in one engine (scheduler loops over 1024-thread
+    # blocks of rows, 32 GEMM tiles per step, 8192-row attention prefix)
+    dict(B=8192, S=64, d=128, V=1024, n_blocks=8192 * 4 + 512, n_req=8192 + 600, lo=1, hi=30, R=1),
 ]
 
 
@@ -54,10 +57,15 @@ CASES = [
 @pytest.mark.parametrize("compat", [0, 1])
 def test_tc_engine_matches_cpu_oracle(torch_cuda, tc, case, compat):
     torch = torch_cuda
+    if case["B"] > 4096 and compat == 1:
+        pytest.skip("with 8800 requests a 3xTF32 tie flip is likely, and the float64 tie classifier "
+                    "replays the corrected decoding, not the stale-lengths quirk")
     w = H.make_weights(41, case["d"], case["V"], case["S"], "Z")
     offs, toks = H.make_prompts(43, case["n_req"], case["lo"], case["hi"], V=case["V"])
     mine, order, st = run_mli_engine(tc, torch, case, w, offs, toks, compat=compat)
-    rc, want, oorder, ost = H.run_oracle_engine("paged", case, w, offs, toks, fix=1 - compat, threads=8)
+    import os
+    rc, want, oorder, ost = H.run_oracle_engine("paged", case, w, offs, toks, fix=1 - compat,
+                                                threads=min(16, os.cpu_count() or 8))
     assert rc == 0
     assert st.n_finished == case["n_req"]
     assert (st.steps, st.generated_tokens, st.preemptions) == (ost.steps, ost.generated_tokens,
