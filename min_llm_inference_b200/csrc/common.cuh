@@ -172,8 +172,6 @@ enum WsSlot {
     WS_QOUT,           // q_output when the caller passes NULL
     WS_ATTN_OUT,       // attention_result when the caller passes NULL
     WS_QKT,            // dense-path score scratch
-    WS_GEMM_A,         // tcgen05 path: dense activation staging
-    WS_GEMM_C,         // tcgen05 path: dense output staging
     WS_NUM_SLOTS
 };
 }  // namespace mli

@@ -254,16 +254,29 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                 cur = g0;
                 open_slice = true;
             }
-            while (next_seg(cur, sg)) {
+            // The iterator runs one segment ahead: the page pointers of the next segment are loaded
+            // while the current one streams.  A bandwidth-bound ring cannot win back an issue gap, and
+            // with rows of a few dozen positions every segment boundary used to open one (measured:
+            // ~2000 cycles per segment).
+            AttnSeg sg_nx;
+            bool have = next_seg(cur, sg);
+            auto first_pages = [&](const AttnSeg& g) -> const float* {
+                const int pg = g.p0 / kPage + lane;
+                return (pg * kPage < g.p1) ? page_table[(size_t)g.r * W + pg] : nullptr;
+            };
+            const float* pages_cur = have ? first_pages(sg) : nullptr;
+            while (have) {
+                const bool have_nx = next_seg(cur, sg_nx);
+                const float* pages_nx = have_nx ? first_pages(sg_nx) : nullptr;
                 const int r = sg.r, p1 = sg.p1;
-                // page pointers are fetched 32 pages at a time: lane i holds page (pgb + i)
-                int pgb = -(1 << 30);
-                const float* my_page = nullptr;
+                // page pointers are held 32 pages at a time: lane i holds page (pgb + i)
+                int pgb = sg.p0 / kPage;
+                const float* my_page = pages_cur;
                 for (int pos = sg.p0; pos < p1; pos += G, ++it) {
                     const int stage = it % nstage;
                     const uint32_t parity = (it / nstage) & 1u;
                     const int nvalid = min(G, p1 - pos);
-                    if (pos / kPage < pgb || (pos + nvalid - 1) / kPage >= pgb + 32) {
+                    if ((pos + nvalid - 1) / kPage >= pgb + 32) {
                         pgb = pos / kPage;
                         const int pg = pgb + lane;
                         my_page = (pg * kPage < p1) ? page_table[(size_t)r * W + pg] : nullptr;
@@ -287,6 +300,9 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                                  (uint32_t)row_floats * 4u, &full_bar[stage]);
                     }
                 }
+                sg = sg_nx;
+                pages_cur = pages_nx;
+                have = have_nx;
             }
             if constexpr (!FUSED) break;
             if (n_slices == (int)gridDim.x) break;   // no dynamic slices in this launch
@@ -318,6 +334,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         }
     }
     uint32_t it = 0;
+    int n_seg_dbg = 0;
     // Partial rows are merged by whoever completes a row's last segment, in slice order.  The
     // fence / atomic / merge latency is kept off the K|V pipeline: rows are queued and flushed after
     // the CTA has run out of slices (or when the queue is full).
@@ -569,6 +586,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         }
 
         // ---- segment epilogue ----
+        ++n_seg_dbg;
         ATTN_STAMP(5);
         const int nseg = sg.nseg;
         const size_t pidx = (size_t)sg.pidx;
@@ -619,11 +637,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         }
     }
     ATTN_STAMP(6);
-    if (dbg != nullptr && threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        dbg[(size_t)blockIdx.x * 8 + 7] = smid;
-    }
+    if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 8 + 7] = ((long long)n_seg_dbg << 32) | it;
 #undef ATTN_STAMP
 }
 
@@ -693,6 +707,8 @@ static int plan_attention(mli_ctx* ctx, int B, int S, int d, bool fused, AttnPla
     if (p->NC == 3) p->NC = 4;
     int G = 1;
     while (G < 16 && 2 * G * d <= 4096) G <<= 1;  // G*d <= 4096 floats of K per stage
+    // (halving the stage for short contexts was measured: 16 KB stages run at 9 B/cycle per CTA against
+    // 12 for 32 KB ones -- the consumers' per-stage barrier / shuffle / exp chain does not shrink)
     p->G = G;
     const size_t stage_bytes = (size_t)G * 2 * d * 4;
     int ctas = ctx->attn_ctas_per_sm > 0 ? ctx->attn_ctas_per_sm : 2;
@@ -794,6 +810,7 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     MLI_ATTN_CASE(1, 8)
     MLI_ATTN_CASE(1, 4)
     MLI_ATTN_CASE(1, 2)
+    MLI_ATTN_CASE(1, 1)
     MLI_ATTN_CASE(2, 2)
     MLI_ATTN_CASE(2, 1)
     MLI_ATTN_CASE(4, 1) {

@@ -519,14 +519,12 @@ struct mli_engine {
     cudaGraph_t graphn = nullptr;
     int n_req = 0;
     mli_engine_stats stats{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_submit = nullptr, ev_end = nullptr;  // job timing: start of submit .. end of run
     bool submit_timed = false;
     cudaEvent_t ring_ev[4] = {};
     int launches_per_step = 0;     // kernels in the captured step graph
     cudaEvent_t prof_ev[32] = {};  // profile mode: one event pair per step of a batch
     int* prof_lengths = nullptr;   // pinned [16][B], profile mode
-    int* lengths_host = nullptr;   // pinned
     // the engine runs on its own non-blocking stream: the caller's stream may be the legacy
     // default stream, which cannot be captured into a graph
     cudaStream_t stream = nullptr;
@@ -740,11 +738,7 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), e->done_host, 0);
         a.done_host = dptr;
         *e->done_host = 0;
-        cudaHostAlloc(reinterpret_cast<void**>(&e->lengths_host), sizeof(int) * (size_t)B,
-                      cudaHostAllocDefault);
     }
-    cudaEventCreate(&e->ev0);
-    cudaEventCreate(&e->ev1);
     cudaEventCreate(&e->ev_submit);
     cudaEventCreate(&e->ev_end);
     for (auto& ev : e->ring_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -784,12 +778,9 @@ int mli_engine_destroy(mli_engine* e) {
     if (e->own_pool && e->pool) cudaFree(e->pool);
     if (e->stage_buf) cudaFree(e->stage_buf);
     if (e->done_host) cudaFreeHost(e->done_host);
-    if (e->lengths_host) cudaFreeHost(e->lengths_host);
     if (e->prof_lengths) cudaFreeHost(e->prof_lengths);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
-    if (e->ev0) cudaEventDestroy(e->ev0);
-    if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_submit) cudaEventDestroy(e->ev_submit);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     for (auto& ev : e->ring_ev)

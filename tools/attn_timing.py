@@ -3,6 +3,7 @@
 bench workload's in-job shape: B=256, d=1024, S=128, lengths like a mid-job engine step.
 Diagnostic tool, not a benchmark.      python tools/attn_timing.py [B d S meanL]
 """
+import os
 import sys
 from pathlib import Path
 
@@ -22,10 +23,9 @@ def main():
     B, d, S, frac = (int(x) for x in sys.argv[1:5]) if len(sys.argv) >= 5 else (256, 1024, 128, 58)
     torch.cuda.set_device(0)
     ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
-    import os
     if os.environ.get("ATTN_CTAS"):
         ctx.set_option(mli.OPT_ATTN_CTAS_PER_SM, int(os.environ["ATTN_CTAS"]))
-    rng = np.random.default_rng(0)
+    rng = np.random.default_rng(int(os.environ.get("ATTN_SEED", "0")))
     L = rng.integers(1, S - 1, size=B).astype(np.int32)
     L[rng.random(B) > frac / 100.0] = 0          # ~58 % of rows active, as in the bench job
     case = H.PagedCase(1, B, S, d, L, "Z")
@@ -86,15 +86,16 @@ def main():
     start0 = st[:, 0].min()
     print("kernel span (first CTA start .. last CTA end, cycles; SM clocks are not synchronised):",
           int(st[:, 6].max() - start0))
-    order = np.argsort(-t_tot)[:12]
-    print("slowest CTAs (cta, smid, total, first, main):")
-    for i in order:
-        print("   ", i, int(smid[i]), int(t_tot[i]), int(st[i, 4] - st[i, 3]) if st[i, 4] else -1,
-              int(st[i, 5] - st[i, 4]) if st[i, 4] else -1)
-    per_sm = {}
-    for i in range(len(st)):
-        per_sm.setdefault(int(smid[i]), []).append(i)
-    print("CTAs per SM histogram:", np.bincount([len(v) for v in per_sm.values()]))
+    nseg, nstage = (smid >> 32)[have], (smid & 0xffffffff)[have]
+    # main-loop time ~ a * stages + b * segments + c  (least squares over the CTAs)
+    A = np.stack([nstage, nseg, np.ones_like(nseg)], axis=1).astype(np.float64)
+    coef, *_ = np.linalg.lstsq(A, t_main, rcond=None)
+    print(f"main loop ~ {coef[0]:.0f} cyc/stage + {coef[1]:.0f} cyc/segment + {coef[2]:.0f}   "
+          f"(stages per CTA {nstage.min()}..{nstage.max()}, segments {nseg.min()}..{nseg.max()})")
+    order = np.argsort(-t_main)[:8]
+    print("slowest main loops (stages, segments, cycles):", [(int(nstage[i]), int(nseg[i]), int(t_main[i])) for i in order])
+    order = np.argsort(t_main)[:8]
+    print("fastest main loops (stages, segments, cycles):", [(int(nstage[i]), int(nseg[i]), int(t_main[i])) for i in order])
     dl = np.diff(st, axis=1).astype(np.float64)
     print(f"{len(st)} CTAs stamped (cold L2)")
     for i, nm in enumerate(NAMES):
