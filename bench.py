@@ -280,6 +280,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference CUDA / long-context legs")
+    ap.add_argument("--no-large", action="store_true", help="skip the engine jobs at the configs[2] / configs[3] shapes")
     ap.add_argument("--pdl", type=int, default=-1, help="override MLI_OPT_PDL (1 programmatic dependent launch, 0 off)")
     ap.add_argument("--gemm-mode", type=int, default=-1, help="override MLI_OPT_GEMM_MODE (0 tcgen05, 1 SIMT exact)")
     args = ap.parse_args()
@@ -459,6 +460,18 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_leg()
             except Exception as e:
                 line["cpu_baseline"] = {"error": str(e)[:200]}
+            if not args.no_large:
+                # the same engine in the HBM-bound regime (not the headline workload): whole jobs at the
+                # BASELINE configs[2] shape and a 32k-context decode at the configs[3] shape
+                sys.path.insert(0, str(REPO / "tools"))
+                eng.close()
+                for key, preset in (("engine_configs2", "c3"), ("engine_configs3", "c4")):
+                    try:
+                        import run_config
+                        torch.cuda.empty_cache()
+                        line[key] = run_config.run(preset, local_rank, reps=1)
+                    except Exception as e:
+                        line[key] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     eng.close()
     ctx.close()

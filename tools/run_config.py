@@ -27,13 +27,12 @@ PRESETS = {
 }
 
 
-def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+def run(name, device=0, reps=2):
     p = PRESETS[name]
     B, d, S, V = p["B"], p["d"], p["S"], p["V"]
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(device)
     peak = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
-    ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
+    ctx = mli.Context(device, torch.cuda.current_stream().cuda_stream)
     page_bytes = 16 * 3 * d * 4
     n_blocks = int(p["pool_gb"] * 1e9 // page_bytes)
     w = H.make_weights(1001, d, V, S, "Z")
@@ -67,7 +66,7 @@ def main():
                    step_floor_ms=1e3 * attn_bytes / (peak * 1e9),
                    whole_step_GBps=attn_bytes / (dt / p["max_steps"]) / 1e9, hbm_peak_GBps=peak)
     else:
-        for rep in range(2):
+        for rep in range(reps):
             eng.submit(d_offs, d_toks, is_device=True)
             eng.run()
             st = eng.stats()
@@ -80,10 +79,10 @@ def main():
         out.update(attention_GBps=ps.attn_bytes / max(ps.attn_ms, 1e-9) / 1e6, hbm_peak_GBps=peak,
                    attention_share_of_job=ps.attn_ms / max(ps.gpu_ms, 1e-9),
                    attention_ms_per_launch=ps.attn_ms / max(1, ps.attn_launches))
-    print(json.dumps(out), flush=True)
     eng.close()
     ctx.close()
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(sys.argv[1] if len(sys.argv) > 1 else "c3")), flush=True)
