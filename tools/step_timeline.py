@@ -60,9 +60,13 @@ def main():
     tl = full[:, :6].astype(np.float64)
     n_act, n_gran = full[:, 6].astype(np.int64), full[:, 7].astype(np.int64)
     real = int(st.steps)
-    # duration of kernel k of step i = stamp of the next kernel - its own stamp
-    nxt = np.concatenate([tl[:, 1:], np.vstack([tl[1:, :1], [[np.nan]]])], axis=1)
-    dur = (nxt - tl)[:real - 1] / 1e3
+    # duration of kernel k of step i = stamp of the next kernel - its own stamp; kernels that are
+    # not part of the graph (e.g. the encoder once it is folded into the GEMM) have no stamps
+    present = [k for k in range(6) if tl[:real - 1, k].any()]
+    dur = np.full((real - 1, 6), np.nan)
+    for a, k in enumerate(present):
+        nxt = tl[:real - 1, present[a + 1]] if a + 1 < len(present) else tl[1:real, 0]
+        dur[:, k] = (nxt - tl[:real - 1, k]) / 1e3
     lines = [f"# In-graph step timeline, bench workload (B={B}, d={d}, S={S}), pdl={args.pdl}",
              "",
              f"{real} engine iterations, {st.generated_tokens} tokens, device job time {st.gpu_ms:.2f} ms "
@@ -74,6 +78,9 @@ def main():
     for k, name in enumerate(SLOTS):
         col = dur[:, k]
         col = col[~np.isnan(col)]
+        if not len(col):
+            lines.append(f"| {name} | - | - | - | not a separate kernel |")
+            continue
         lines.append(f"| {name} | {col.mean():.1f} | {np.median(col):.1f} | {np.percentile(col, 90):.1f} | "
                      f"{100 * col.mean() / tot:.1f}% |")
     lines.append(f"\nSum of means {tot:.1f} us per iteration.")
@@ -87,7 +94,7 @@ def main():
         if m.any():
             lines.append(f"| {lo}-{hi if hi < 1 << 30 else 'inf'} | {int(m.sum())} | {g[m].mean():.1f} | "
                          f"{n_act[:real - 1][m].mean():.0f} | {n_gran[:real - 1][m].mean():.1f} |")
-    e = dur[:, 1]
+    e = dur[:, 1] if 1 in present else np.full(real - 1, np.nan)
     for has in (False, True):
         m = ((n_gran[:real - 1] > 0) == has) & ~np.isnan(e)
         if m.any():
