@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "libmli_b200.so"
+LIB_PATH = Path(os.environ.get("MLI_B200_LIB", PKG_DIR / "libmli_b200.so"))   # override: A/B builds
 
 OPT_GEMM_MODE = 1
 OPT_ATTN_CHUNK_PAGES = 2

@@ -151,7 +151,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     }
     __syncthreads();
     griddep_wait();
-    griddep_launch_dependents();
+    GRIDDEP_TRIGGER_EARLY();
     trace_stamp(trace, 3);
     ATTN_STAMP(1);
 
@@ -625,6 +625,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     }
     if constexpr (!FUSED) break;
     }   // slices
+    GRIDDEP_TRIGGER_LATE();
     flush_pending();
     if constexpr (FUSED) {
         // the last CTA to finish re-arms the slice counter for the next launch

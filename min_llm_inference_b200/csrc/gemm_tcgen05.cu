@@ -352,7 +352,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
     griddep_wait();
-    griddep_launch_dependents();
+    GRIDDEP_TRIGGER_EARLY();
     trace_stamp(args.trace, args.trace_slot);
 
     const int n_valid = tc_n_valid(args);
@@ -549,6 +549,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         it += (uint32_t)kb_per;
         ++tile_iter;
     }
+    GRIDDEP_TRIGGER_LATE();
     if (tile_iter == 0 && warp == 0 && lane == 0) {
         // nothing to do after all: the prefetched weight tiles must land before the CTA may exit
         for (int i = 0; i < n_pre; ++i) mbar_wait(&full_w[i], 0);

@@ -86,7 +86,7 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
     const int W = S / kPage, d4 = d >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     griddep_wait();
-    griddep_launch_dependents();
+    GRIDDEP_TRIGGER_EARLY();
     trace_stamp(trace, 1);
     const int nt = *n_tiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
@@ -136,6 +136,7 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
             }
         }
     }
+    GRIDDEP_TRIGGER_LATE();
 }
 
 int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos, const int* inp,
