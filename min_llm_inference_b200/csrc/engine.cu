@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int* s_list = s_flag + B;                                     // [B] need list / free rows
     int* s_len = s_list + B;                                      // [B] device lengths as the model kernels will see them
     griddep_wait();
-    griddep_launch_dependents();
+    GRIDDEP_TRIGGER_EARLY();
     trace_stamp(a.trace, 0);
 
     // every thread reads the counters itself (one broadcast line) together with its rows' state:
@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         __syncthreads();
     }
 
+    GRIDDEP_TRIGGER_LATE();
     // ---- write the mirrors back ----
     for (int r = tid; r < B; r += T) {
         a.row_req[r] = s_req[r];

@@ -26,6 +26,7 @@
 
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -731,11 +732,15 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     if (rows <= 0) return 0;
     // expect_rows: rows the launch will typically see (prefill: device-side count, usually small)
     long long plan_rows = expect_rows > 0 ? std::min<long long>(rows, expect_rows) : rows;
-    const int n_tiles_plan = (int)((plan_rows + kMaxBN - 1) / kMaxBN);
+    // deferred-reduce launches (logits) are all fixed cost around a tiny main loop: narrower tiles
+    // halve the TMEM -> smem -> global epilogue per CTA
+    // per CTA and the number of partial planes the decoder sums (measured: decoder 5.9 -> 4.9 us)
+    const int max_bn = args.defer ? 128 : kMaxBN;
+    const int n_tiles_plan = (int)((plan_rows + max_bn - 1) / max_bn);
     long long per_tile = (plan_rows + n_tiles_plan - 1) / n_tiles_plan;
     int bn = (int)((per_tile + 15) / 16 * 16);
-    if (bn > kMaxBN) bn = kMaxBN;
-    if (rows > plan_rows) bn = kMaxBN;            // the device count may exceed the plan: full-width tiles
+    if (bn > max_bn) bn = max_bn;
+    if (rows > plan_rows) bn = max_bn;            // the device count may exceed the plan: full-width tiles
     const int n_tiles_all = (int)((rows + bn - 1) / bn);
     const int num_kb = args.K / kBK;
     int split = 1;
