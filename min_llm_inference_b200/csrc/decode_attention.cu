@@ -156,17 +156,20 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     ATTN_STAMP(1);
 
     int n_items = 0;      // legacy: number of (row, chunk) items
-    // fused: the flattened position space [0, P) is cut into gridDim.x STATIC slices of qs positions
-    // (CTA b starts with slice b: ~3/4 of a fair share) followed by DYNAMIC slices of qd positions
-    // that CTAs claim from a global counter as they run dry -- faster SMs take more of the tail.
+    // fused: the work is flattened in units of pipeline STAGES (G positions of one row; the last
+    // stage of a row may be partial).  Measured: a CTA's streaming time is proportional to its number
+    // of stages, not to its bytes (2750 cycles per stage, full or not), so slices hold equal numbers
+    // of stages.  The space [0, P) is cut into gridDim.x STATIC slices of qs stages (CTA b starts
+    // with slice b: a fair share, or ~3/4 of it when shares are large) followed by DYNAMIC slices of
+    // qd stages that CTAs claim from a global counter as they run dry.
     int qs = 1, qd = 1, dyn0 = 0, n_slices = 0, P = 0;
     if constexpr (FUSED) {
-        // exclusive prefix of the lengths, kAttnThreads rows at a time
+        // exclusive prefix of the rows' stage counts, kAttnThreads rows at a time
         if (tid == 0) scan_tmp[12] = 0;
         __syncthreads();
         for (int base = 0; base < B; base += kAttnThreads) {
             const int r = base + tid;
-            const int n = (r < B) ? lengths[r] : 0;
+            const int n = (r < B) ? (lengths[r] + G - 1) / G : 0;
             int v = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -190,10 +193,10 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         // small problems (a fair share of a few dozen positions) are split statically: dynamic
         // slices would be a single pipeline stage each and their claims / merges cost more than
         // the tail they remove
-        qs = (fair >= kMinDynFair) ? max(G, (fair * 3 / 4) / G * G) : max(G, (fair + G - 1) / G * G);
+        qs = (fair * G >= kMinDynFair) ? max(1, fair * 3 / 4) : max(1, fair);
         dyn0 = (int)min((long long)P, (long long)grid * qs);
         const int dyn = P - dyn0;
-        qd = max(G, ((dyn + 3 * grid - 1) / (3 * grid) + G - 1) / G * G);
+        qd = max(1, (dyn + 3 * grid - 1) / (3 * grid));
         n_slices = grid + (dyn + qd - 1) / qd;
     } else {
         n_items = row_first_g[B];
@@ -204,9 +207,9 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     auto slice_of = [&](int pos) -> int {
         return pos < dyn0 ? pos / qs : (int)gridDim.x + (pos - dyn0) / qd;
     };
-    int slice = 0, g0 = 0, g1 = 0;   // fused: current slice and its position range
+    int slice = 0, g0 = 0, g1 = 0;   // fused: current slice and its range of stages
 
-    // work iterator, identical in the producer and the consumers.  `cur` is a global position
+    // work iterator, identical in the producer and the consumers.  `cur` is a global stage index
     // (fused) or an item index (legacy).
     auto next_seg = [&](int& cur, AttnSeg& sg) -> bool {
         if constexpr (FUSED) {
@@ -216,13 +219,14 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                 const int mid = (lo + hi) >> 1;
                 if (pos_first[mid] <= cur) lo = mid; else hi = mid;
             }
-            const int start = pos_first[lo], L = pos_first[lo + 1] - start;
+            const int start = pos_first[lo], n_st = pos_first[lo + 1] - start;   // in stages
+            const int st1 = min(g1 - start, n_st);
             sg.r = lo;
-            sg.p0 = cur - start;
-            sg.p1 = min(g1 - start, L);
-            sg.nseg = slice_of(start + L - 1) - slice_of(start) + 1;
+            sg.p0 = (cur - start) * G;
+            sg.p1 = min(st1 * G, lengths[lo]);   // only the row's last stage can be partial
+            sg.nseg = slice_of(start + n_st - 1) - slice_of(start) + 1;
             sg.pidx = 2 * slice + (cur == g0 ? 0 : 1);
-            cur = start + sg.p1;
+            cur = start + st1;
             return true;
         } else {
             if (cur >= n_items) return false;
