@@ -63,10 +63,14 @@ struct SchedArgs {
 constexpr int kSchedThreads = 1024;
 constexpr int kGran = kPage;   // positions per prefill granule
 
-// exclusive block scan; every thread must call it.  total = sum over the block.
-__device__ int block_scan_excl(int v, int* total, int* s_warp) {
+// exclusive block scan; every thread must call it.  total = sum over the block.  s_warp is
+// [2][32]: consecutive calls alternate between the halves, so a call needs two barriers, not three
+// (the half a call writes was last read two barriers ago).
+__device__ int block_scan_excl(int v, int* total, int* s_warp2, int& phase) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
+    int* s_warp = s_warp2 + 32 * (phase & 1);
+    ++phase;
     int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -75,20 +79,16 @@ __device__ int block_scan_excl(int v, int* total, int* s_warp) {
     }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    if (warp == 0) {
-        int w = (lane < nwarps) ? s_warp[lane] : 0;
+    // every warp scans the (at most 32) warp totals itself: no second hand-off through shared memory
+    int w = (lane < nwarps) ? s_warp[lane] : 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        s_warp[lane] = w;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
     }
-    __syncthreads();
-    const int res = x - v + (warp > 0 ? s_warp[warp - 1] : 0);
-    *total = s_warp[nwarps - 1];
-    __syncthreads();
-    return res;
+    const int before = (warp > 0) ? __shfl_sync(0xffffffffu, w, warp - 1) : 0;
+    *total = __shfl_sync(0xffffffffu, w, nwarps - 1);
+    return x - v + before;
 }
 
 // shared-memory footprint of the scheduler: six int arrays of B entries and the free-page window
@@ -105,8 +105,9 @@ size_t sched_smem_bytes(int B) {
 // pre-empt the list tail when the pool is dry) runs without dependent global-memory round trips.
 __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) {
     extern __shared__ __align__(16) unsigned char sched_smem[];
-    __shared__ int s_warp[32];
+    __shared__ int s_warp[64];
     __shared__ int s_carry[4];
+    int scan_phase = 0;
     __shared__ long long s_pre;
     const int tid = threadIdx.x, T = blockDim.x;
     const int B = a.B, S = a.S, W = a.W, R = a.R;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             const int r = base + tid;
             const int f = (r < B) ? (s_flag[r] & 1) : 0;
             int tot;
-            const int pos = block_scan_excl(f, &tot, s_warp);
+            const int pos = block_scan_excl(f, &tot, s_warp, scan_phase);
             if (f) {
                 a.fin_ids[n_fin + pos] = s_req[r];
                 s_req[r] = -1;
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                     np = rel ? s_np[row] : 0;
                 }
                 int totp, totk;
-                const int ppos = block_scan_excl(np, &totp, s_warp);
-                const int kpos = block_scan_excl(keep, &totk, s_warp);
+                const int ppos = block_scan_excl(np, &totp, s_warp, scan_phase);
+                const int kpos = block_scan_excl(keep, &totk, s_warp, scan_phase);
                 // every read of s_used[] in this chunk is done (the scans contain barriers)
                 if (rel) {
                     const int o = fh + F + freed + ppos;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                     need = ((s_flag[row] >> 2) + R > s_np[row] * kPage) ? 1 : 0;   // count from phase 1
                 }
                 int tot;
-                const int pos = block_scan_excl(need, &tot, s_warp);
+                const int pos = block_scan_excl(need, &tot, s_warp, scan_phase);
                 if (need) s_list[m + pos] = i;
                 m += tot;
             }
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             const int r = base + tid;
             const int fr = (r < B && !s_flag[r]) ? 1 : 0;
             int tot;
-            const int pos = block_scan_excl(fr, &tot, s_warp);
+            const int pos = block_scan_excl(fr, &tot, s_warp, scan_phase);
             if (fr) s_list[n_free_rows + pos] = r;
             n_free_rows += tot;
         }
@@ -341,10 +342,10 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 need = max((len + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
             }
             int totn;
-            const int before = need_before + block_scan_excl(need, &totn, s_warp);
+            const int before = need_before + block_scan_excl(need, &totn, s_warp, scan_phase);
             const int admit = (j < n_cand && before + need <= F) ? 1 : 0;
             int tota;
-            (void)block_scan_excl(admit, &tota, s_warp);
+            (void)block_scan_excl(admit, &tota, s_warp, scan_phase);
             if (admit) {
                 const int row = s_list[j];
                 const int np = min(need, W);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         const int r = base + tid;
         const int on = (r < B && s_len[r] > 0) ? 1 : 0;
         int tot;
-        const int pos = block_scan_excl(on, &tot, s_warp);
+        const int pos = block_scan_excl(on, &tot, s_warp, scan_phase);
         if (on) a.act_rows[n_act + pos] = r;
         n_act += tot;
     }
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             n = (s_len[row] + kGran - 1) / kGran;
         }
         int tot;
-        const int pos = block_scan_excl(n, &tot, s_warp);
+        const int pos = block_scan_excl(n, &tot, s_warp, scan_phase);
         for (int c = 0; c < n; ++c) {
             if (n_gran + pos + c < a.max_gran) {
                 a.gran[n_gran + pos + c].row = row;
