@@ -248,6 +248,10 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     if (warp == kConsumerWarps) {
         // ===================== producer warp =====================
         uint32_t it = 0;  // running stage counter across segments
+        // K|V rows are read once per step and the cache of a step (~100 MB on the bench job) is as
+        // large as the L2: mark them evict-first so that they do not flush what IS re-read every
+        // step (the split weights, the scheduler's state, the work lists)
+        const uint64_t kv_policy = l2_policy_evict_first();
         slice = (int)blockIdx.x;
         for (;;) {
             bool open_slice = false;
@@ -300,8 +304,8 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_page), pg));
                     if (lane < nvalid) {
                         const float* src = page + (size_t)(j & (kPage - 1)) * 3 * d + d;
-                        bulk_g2s(ring + (size_t)stage * stage_floats + (size_t)lane * row_floats, src,
-                                 (uint32_t)row_floats * 4u, &full_bar[stage]);
+                        bulk_g2s_hint(ring + (size_t)stage * stage_floats + (size_t)lane * row_floats, src,
+                                      (uint32_t)row_floats * 4u, &full_bar[stage], kv_policy);
                     }
                 }
                 sg = sg_nx;

@@ -52,6 +52,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// the same with an L2 cache hint (the split weights are re-read every step: evict-last)
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                 uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -343,12 +352,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // The weights are static: the producer starts filling the pipeline with weight tiles right away,
     // before this kernel is allowed to look at anything its predecessor wrote.
     const int n_pre = min(nst, kb_per);
+    const uint64_t w_policy = l2_policy_evict_last();
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < n_pre; ++i) {
             unsigned char* st = base + (size_t)i * stage_bytes;
             mbar_expect_tx(&full_w[i], 2 * kWBytes);
-            tma_load_2d(st, &map_a_hi, (kb0 + i) * kBK, m0, &full_w[i]);
-            tma_load_2d(st + kWBytes, &map_a_lo, (kb0 + i) * kBK, m0, &full_w[i]);
+            tma_load_2d_hint(st, &map_a_hi, (kb0 + i) * kBK, m0, &full_w[i], w_policy);
+            tma_load_2d_hint(st + kWBytes, &map_a_lo, (kb0 + i) * kBK, m0, &full_w[i], w_policy);
         }
     }
     // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
@@ -386,8 +396,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     mbar_wait(&empty_bar[s], ((i / nst) & 1) ^ 1);
                     unsigned char* st = base + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full_w[s], 2 * kWBytes);
-                    tma_load_2d(st, &map_a_hi, kb * kBK, m0, &full_w[s]);
-                    tma_load_2d(st + kWBytes, &map_a_lo, kb * kBK, m0, &full_w[s]);
+                    tma_load_2d_hint(st, &map_a_hi, kb * kBK, m0, &full_w[s], w_policy);
+                    tma_load_2d_hint(st + kWBytes, &map_a_lo, kb * kBK, m0, &full_w[s], w_policy);
                 }
             }
             __syncwarp();
