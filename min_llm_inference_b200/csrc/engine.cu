@@ -246,6 +246,31 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             const int n_win = min(min(F, m), n_fq);
             for (int j = tid; j < n_win; j += T) fq[j] = a.free_ring[(fh0 + j) % nb];
             __syncthreads();
+            if (F >= m) {
+                // every row that needs a page finds one: no pre-emption can happen and the pages are
+                // handed out by a scan (row k of the need list takes the k-th free page it is due)
+                int taken = 0;
+                for (int base = 0; base < m; base += T) {
+                    const int k = base + tid;
+                    int row = -1, np = 0, take = 0;
+                    if (k < m) {
+                        row = s_used[s_list[k]];
+                        np = s_np[row];
+                        take = (np < W) ? 1 : 0;   // allocate_memory_block (:196-203): new page at index size-1
+                    }
+                    int tot;
+                    const int idx = taken + block_scan_excl(take, &tot, s_warp, scan_phase);
+                    if (take) {
+                        a.page_table[(size_t)row * W + np] =
+                            (idx < n_fq) ? fq[idx] : a.free_ring[(fh0 + idx) % nb];
+                        s_np[row] = np + 1;
+                    }
+                    taken += tot;
+                }
+                F -= taken;
+                fh = (fh + taken) % nb;
+                __syncthreads();
+            } else {
             if (tid == 0) {
                 int n = n_used, taken = 0;   // taken = window entries consumed so far
                 long long pre = 0;
@@ -308,6 +333,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             qh = s_carry[3];
             sv.preemptions += s_pre;
             __syncthreads();
+            }
         }
     }
 
