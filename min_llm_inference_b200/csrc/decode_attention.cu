@@ -7,18 +7,19 @@
 // and its [B,S] score round-trips with one pass over K and V.
 //
 // Design (HBM-bound; SURVEY 8d: ATTN_BYTES = sum_r 8*d*L_r + 8*d + 8*ceil(L_r/16) + 4):
-//   * work item = (row, chunk of CH pages); a tiny prep kernel lists the items from the device
-//     lengths, persistent CTAs (a multiple of the SM count) walk the list round-robin;
+//   * ONE launch: persistent CTAs (a multiple of the SM count) each take slices of the flattened
+//     work (in units of pipeline stages) derived inside the kernel from the device lengths;
 //   * one producer warp streams K|V rows (they are adjacent inside a page: [inp|K|V] per
 //     position, so one 8*d-byte bulk copy per position) into a shared-memory ring with
 //     cp.async.bulk + mbarrier complete_tx (TMA, non-tensor form -- page tables hold raw pointers,
-//     so a tensor map cannot follow them); page pointers of the chunk are fetched once per item
-//     and handed round by warp shuffle;
+//     so a tensor map cannot follow them), marked L2::evict_first; the page pointers of the next
+//     segment are fetched while the current one streams;
 //   * eight consumer warps: each thread owns float4 columns of d; q.K partial dots are reduced by
 //     warp shuffle + a small shared array; online softmax (running max / sum) in fp32;
 //     P.V accumulates in registers; K and V are each read exactly once from HBM;
-//   * split partials (m, l, acc[d]) are merged by a small combine kernel which also zero-fills
-//     empty rows and (optionally) materialises the reference's [B,S] probabilities.
+//   * rows cut by a slice boundary leave (m, l, acc[d]) partials that the CTA completing the row
+//     merges; empty rows are zero-filled; a three-launch variant (prep, main, combine) also
+//     materialises the reference's [B,S] probabilities for the tests.
 // Scale is dot / sqrtf(d) (a division, paged_attention.cu:261) and the exponent is expf, as in
 // the reference.
 #include "common.cuh"
@@ -91,11 +92,12 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // main kernel
 // ---------------------------------------------------------------------------------------------
 // FUSED = true (the production path, ONE launch per decode step): every CTA scans the lengths into
-// a shared-memory prefix over POSITIONS and takes an equal, contiguous slice of the flattened
-// position space (stream-K style: bytes per CTA are balanced exactly, whatever the mix of row
-// lengths).  A slice may start or end inside a row; such partial rows (at most two per CTA: its
-// head and its tail) are merged by whichever CTA finishes the row's last segment (per-row arrival
-// counter in global memory, self-resetting).  B <= kMaxFusedRows.
+// a shared-memory prefix over pipeline STAGES (G positions of one row) and takes equal, contiguous
+// slices of the flattened stage space (stream-K style: the streaming time of a CTA is proportional
+// to its number of stages, so slices are balanced whatever the mix of row lengths).  A slice may
+// start or end inside a row; such partial rows (at most two per slice: its head and its tail) are
+// merged by whichever CTA finishes the row's last segment (per-row arrival counter in global
+// memory, self-resetting).  B <= kMaxFusedRows.
 // FUSED = false: (row, chunk) items from attn_prep_kernel, merge by attn_combine_kernel -- used when
 // the [B,S] probabilities are requested or B is too large for the shared-memory prefix.
 constexpr int kMaxFusedRows = 8192;
@@ -119,7 +121,8 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         float* __restrict__ part_ml, float* __restrict__ scores_out,
                         int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage,
                         long long* __restrict__ dbg, unsigned long long* trace) {
-    // optional phase stamps (tools/attn_timing.py): [cta][8] clock64 of consumer thread 0
+    // optional phase stamps (tools/attn_timing.py): [cta][8]; slots 0-6 clock64 of consumer thread 0,
+    // slot 7 = segments << 32 | stages this CTA processed
 #define ATTN_STAMP(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
     ATTN_STAMP(0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -136,7 +139,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     int* pend_r = stage_meta + kMaxStages;                                   // [kMaxPend] partial rows to merge
     int* pend_nseg = pend_r + kMaxPend;
     int* pend_flag = pend_nseg + kMaxPend;
-    int* pos_first = pend_flag + kMaxPend;                                   // FUSED: [B + 1]
+    int* stage_first = pend_flag + kMaxPend;                                   // FUSED: [B + 1]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -180,13 +183,13 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             __syncthreads();
             int before = scan_tmp[12];
             for (int w = 0; w < warp; ++w) before += scan_tmp[w];
-            if (r < B) pos_first[r] = before + v - n;
+            if (r < B) stage_first[r] = before + v - n;
             __syncthreads();
             if (tid == kAttnThreads - 1) scan_tmp[12] = before + v;
             __syncthreads();
         }
         P = scan_tmp[12];
-        if (tid == 0) pos_first[B] = P;
+        if (tid == 0) stage_first[B] = P;
         __syncthreads();
         const int grid = (int)gridDim.x;
         const int fair = (P + grid - 1) / grid;
@@ -214,12 +217,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     auto next_seg = [&](int& cur, AttnSeg& sg) -> bool {
         if constexpr (FUSED) {
             if (cur >= g1) return false;
-            int lo = 0, hi = B;   // largest r with pos_first[r] <= cur (empty rows share a start: skipped)
+            int lo = 0, hi = B;   // largest r with stage_first[r] <= cur (empty rows share a start: skipped)
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (pos_first[mid] <= cur) lo = mid; else hi = mid;
+                if (stage_first[mid] <= cur) lo = mid; else hi = mid;
             }
-            const int start = pos_first[lo], n_st = pos_first[lo + 1] - start;   // in stages
+            const int start = stage_first[lo], n_st = stage_first[lo + 1] - start;   // in stages
             const int st1 = min(g1 - start, n_st);
             sg.r = lo;
             sg.p0 = (cur - start) * G;
@@ -336,7 +339,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     if constexpr (FUSED) {
         // empty rows produce zeros (the reference stores result = 0, paged_attention.cu:289,:323)
         for (int r = blockIdx.x; r < B; r += gridDim.x) {
-            if (pos_first[r + 1] != pos_first[r]) continue;
+            if (stage_first[r + 1] != stage_first[r]) continue;
             for (int col = tid; col < d4; col += kConsumerThreads)
                 reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -360,7 +363,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             for (int pi = 0; pi < n_pend; ++pi) {
                 if (!pend_flag[pi]) continue;
                 const int r = pend_r[pi], nseg = pend_nseg[pi];
-                const int start = pos_first[r];
+                const int start = stage_first[r];
                 const int b_first = slice_of(start);
                 // segment k of the row lives in slice b_first + k: its head slot, except that the
                 // row's first segment is its slice's tail slot unless the row opens that slice
