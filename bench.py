@@ -63,6 +63,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """dense bf16 TFLOP/s (sustained: the GEMM is timed inside a long job); tf32 is half of it"""
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        m = json.loads(f.read_text())
+        return float(m.get("bf16_tflops_sustained", m.get("bf16_tflops", 1400.0))), "measured (MEASURED_PEAKS.json)"
+    return 1400.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -443,6 +452,21 @@ def main():
                                  "(14 us at peak), so fixed costs dominate; the same kernel at the configs[2] shape is "
                                  "in roofline_long_context"},
         }
+        if ps.gemm_launches > 0:
+            bf16_peak, tsrc = tensor_peak()
+            tflops = ps.gemm_flops / max(ps.gemm_ms, 1e-9) / 1e9
+            line["roofline_gemm"] = {
+                "kernel": "gemm_tf32x3_kernel (merged latest-token QKV + prefill projection, 3xTF32 on tcgen05)",
+                "bound": "tensor", "achieved": 3.0 * tflops, "peak": bf16_peak / 2.0, "unit": "TFLOP/s",
+                "frac": 3.0 * tflops / (bf16_peak / 2.0), "fp32_equivalent_tflops": tflops,
+                "peak_source": tsrc + ": dense bf16 sustained / 2 = tf32",
+                "launches": ps.gemm_launches, "avg_launch_us": 1e3 * ps.gemm_ms / ps.gemm_launches,
+                "algorithmic_flops_per_launch": ps.gemm_flops / ps.gemm_launches,
+                "note": "achieved = 3 x fp32-equivalent FLOPs (each product is three tf32 MMAs) / CUDA-event time of "
+                        "every launch of one job.  A decode-size launch is ~1 GFLOP (150-250 rows): it is bound by "
+                        "fixed costs, not by the tensor pipe (ncu: pipe active 41 % on the busiest SM during the "
+                        "main loop's share of the kernel, profiles/r1_gemm_ncu.json); by launch share of the step the "
+                        "two GEMMs (46 %) exceed the attention (31 %)"}
         if world == 1 and not args.no_extras:
             try:
                 # its own context: the engine's captured graph pins the first context's workspaces

@@ -199,6 +199,10 @@ typedef struct {
                                    when profiling was requested (else 0) */
     double attn_bytes;          /* algorithmic bytes of those launches (SURVEY 8d ATTN_BYTES) */
     long long attn_launches;
+    float gemm_ms;              /* profiling only: device time of the merged latest-QKV + prefill GEMM */
+    double gemm_flops;          /* fp32-equivalent FLOPs of those launches: 6*d*d per active row +
+                                   4*d*d per prefill position (the tensor cores execute 3x that in tf32) */
+    long long gemm_launches;
 } mli_engine_stats;
 
 typedef struct mli_engine mli_engine;

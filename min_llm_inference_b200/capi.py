@@ -43,6 +43,7 @@ class EngineStats(C.Structure):
         ("steps", _LL), ("generated_tokens", _LL), ("preemptions", _LL), ("admitted", _LL),
         ("n_finished", _I), ("gpu_ms", C.c_float), ("attn_ms", C.c_float),
         ("attn_bytes", C.c_double), ("attn_launches", _LL),
+        ("gemm_ms", C.c_float), ("gemm_flops", C.c_double), ("gemm_launches", _LL),
     ]
 
 

@@ -229,6 +229,7 @@ struct mli_ctx {
     bool ws_frozen = false;     // set while a CUDA graph that captured ws pointers is alive
     // when set, the fused decode-attention main kernel is bracketed by these events (profiling)
     cudaEvent_t attn_ev_start = nullptr, attn_ev_stop = nullptr;
+    cudaEvent_t gemm_ev_start = nullptr, gemm_ev_stop = nullptr;   // same for the step's merged GEMM
 };
 
 namespace mli {

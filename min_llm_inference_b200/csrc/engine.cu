@@ -551,8 +551,9 @@ struct mli_engine {
     bool submit_timed = false;
     cudaEvent_t ring_ev[4] = {};
     int launches_per_step = 0;     // kernels in the captured step graph
-    cudaEvent_t prof_ev[32] = {};  // profile mode: one event pair per step of a batch
-    int* prof_lengths = nullptr;   // pinned [16][B], profile mode
+    cudaEvent_t prof_ev[32] = {};  // profile mode: one event pair per step of a batch (attention)
+    cudaEvent_t prof_gev[32] = {}; // the same for the merged GEMM
+    int* prof_lengths = nullptr;   // pinned [16][B + 2] (lengths, then the scheduler's two counts), profile mode
     // the engine runs on its own non-blocking stream: the caller's stream may be the legacy
     // default stream, which cannot be captured into a graph
     cudaStream_t stream = nullptr;
@@ -595,7 +596,8 @@ int dev_alloc(mli_engine* e, T** out, size_t n) {
 
 // the model part of one engine iteration: n_forward_rounds x (encoder -> attention -> decoder)
 // (inference_model.cpp:52-82).  ev0/ev1, when given, bracket the first round's fused attention.
-int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1) {
+int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t gev0 = nullptr,
+                  cudaEvent_t gev1 = nullptr) {
     mli_ctx* ctx = e->ctx;
     const mli_engine_cfg& c = e->cfg;
     const int B = c.n_batch, S = c.n_sequence, d = c.emb_dim, V = c.n_vocab;
@@ -627,10 +629,16 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1) {
             return rc;
     }
     for (int round = 0; round < c.n_forward_rounds; ++round) {
-        if (tc)
+        if (tc) {
+            if (round == 0 && gev0) {
+                ctx->gemm_ev_start = gev0;
+                ctx->gemm_ev_stop = gev1;
+            }
             rc = launch_step_qkv_tc(ctx, e->a.page_table, e->a.lengths, e->a.act_rows, e->a.counts,
                                     e->a.gran, e->a.max_gran, round == 0 ? 1 : 0, e->wk, e->wq, e->wv,
                                     e->q_out, B, S, d);
+            ctx->gemm_ev_start = ctx->gemm_ev_stop = nullptr;
+        }
         else
             rc = launch_qkv_latest_paged_simt(ctx, e->a.page_table, e->a.lengths, e->wk, e->wq, e->wv,
                                               e->q_out, B, S, d);
@@ -809,6 +817,8 @@ int mli_engine_destroy(mli_engine* e) {
     if (e->prof_lengths) cudaFreeHost(e->prof_lengths);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->prof_gev)
+        if (ev) cudaEventDestroy(ev);
     if (e->ev_submit) cudaEventDestroy(e->ev_submit);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     for (auto& ev : e->ring_ev)
@@ -867,9 +877,9 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     StreamScope scope(e);
     int rc;
     const int B = e->cfg.n_batch, d = e->cfg.emb_dim;
-    float attn_ms = 0.f;
-    double attn_bytes = 0.0;
-    long long attn_launches = 0;
+    float attn_ms = 0.f, gemm_ms = 0.f;
+    double attn_bytes = 0.0, gemm_flops = 0.0;
+    long long attn_launches = 0, gemm_launches = 0;
     MLI_CUDA(cudaEventRecord(e->ring_ev[0], ctx->stream));  // make ring events valid
     // device time of the job: from the start of the submit that fed this run (else from here)
     if (!e->submit_timed) MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
@@ -882,8 +892,9 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
         constexpr int kBatch = 16;
         if (!e->prof_ev[0]) {
             for (auto& ev : e->prof_ev) MLI_CUDA(cudaEventCreate(&ev));
+            for (auto& ev : e->prof_gev) MLI_CUDA(cudaEventCreate(&ev));
             MLI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->prof_lengths),
-                                   sizeof(int) * (size_t)B * kBatch, cudaHostAllocDefault));
+                                   sizeof(int) * ((size_t)B + 2) * kBatch, cudaHostAllocDefault));
         }
         bool finished = false;
         while (!finished) {
@@ -892,14 +903,29 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
                 if (max_steps > 0 && it >= max_steps) { finished = true; break; }
                 sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), ctx->stream>>>(e->a);
                 MLI_LAUNCH_CHECK();
-                MLI_CUDA(cudaMemcpyAsync(e->prof_lengths + (size_t)nb * B, e->a.lengths,
-                                         sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-                if ((rc = enqueue_model(e, e->prof_ev[2 * nb], e->prof_ev[2 * nb + 1]))) return rc;
+                int* slot = e->prof_lengths + (size_t)nb * (B + 2);
+                MLI_CUDA(cudaMemcpyAsync(slot, e->a.lengths, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+                MLI_CUDA(cudaMemcpyAsync(slot + B, e->a.counts, sizeof(int) * 2, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+                if ((rc = enqueue_model(e, e->prof_ev[2 * nb], e->prof_ev[2 * nb + 1], e->prof_gev[2 * nb],
+                                        e->prof_gev[2 * nb + 1])))
+                    return rc;
             }
             MLI_CUDA(cudaStreamSynchronize(ctx->stream));
             for (int k = 0; k < nb; ++k) {
-                const double bytes = attention_algorithmic_bytes(e->prof_lengths + (size_t)k * B, B, d);
+                const int* slot = e->prof_lengths + (size_t)k * (B + 2);
+                const double bytes = attention_algorithmic_bytes(slot, B, d);
                 if (bytes <= 0.0) continue;   // a step past the end of the job: nothing to attend
+                if (ctx->gemm_mode == 0 && ctx->tc_available && d % 128 == 0) {
+                    // active rows: K, q, V of one position; granules: K, V of the new rows' earlier
+                    // positions (a granule is 16 positions, the last one of a row partly used: upper bound)
+                    float gms = 0.f;
+                    MLI_CUDA(cudaEventElapsedTime(&gms, e->prof_gev[2 * k], e->prof_gev[2 * k + 1]));
+                    gemm_ms += gms;
+                    gemm_flops += (6.0 * slot[B] + 4.0 * kPage * slot[B + 1]) * (double)d * d;
+                    ++gemm_launches;
+                }
                 float ms = 0.f;
                 MLI_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]));
                 attn_ms += ms;
@@ -960,6 +986,9 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     e->stats.attn_ms = attn_ms;
     e->stats.attn_bytes = attn_bytes;
     e->stats.attn_launches = attn_launches;
+    e->stats.gemm_ms = gemm_ms;
+    e->stats.gemm_flops = gemm_flops;
+    e->stats.gemm_launches = gemm_launches;
     if (hv.error) {
         set_error("engine: a token arrived for a row that is not processing");
         return MLI_ERR_STATE;

@@ -912,7 +912,11 @@ int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* length
     a.n_rows = (int)std::min<long long>(bound, 1 << 30);
     // a step usually has at most B active rows plus a few short prompts: plan the split for that
     // and let the clusters walk further tiles when an admission wave brings more
-    return run_gemm(ctx, w, a, 3 * d / kBM, std::max(kMaxBN, (B + 15) / 16 * 16));
+    if (ctx->gemm_ev_start) MLI_CUDA(cudaEventRecord(ctx->gemm_ev_start, ctx->stream));
+    rc = run_gemm(ctx, w, a, 3 * d / kBM, std::max(kMaxBN, (B + 15) / 16 * 16));
+    if (rc) return rc;
+    if (ctx->gemm_ev_stop) MLI_CUDA(cudaEventRecord(ctx->gemm_ev_stop, ctx->stream));
+    return 0;
 }
 
 int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* score, int B, int V, int d,
