@@ -761,6 +761,15 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
             break;
         }
     }
+    // accuracy before occupancy: the TMEM holds 512 / bn accumulators, and a single fp32 chain should
+    // not exceed 1024 products (truncating accumulation: 2048-long chains on all-positive data drift
+    // 1.4e-5).  With wide tiles and K >= 2048 that takes a K split even when one wave would not need it.
+    {
+        const int acc_max = std::max(1, 512 / ((bn + 31) / 32 * 32));
+        while (args.K / (split * acc_max) > 1024 && split < (args.defer ? kMaxLogitSplit : 8) &&
+               num_kb % (2 * split) == 0)
+            split *= 2;
+    }
     int ny = n_tiles_all;
     const int cap = std::max(1, ctx->num_sms / (m_tiles * split));
     if (ny > cap) ny = std::max(cap, std::min(n_tiles_plan, n_tiles_all));

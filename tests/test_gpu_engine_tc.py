@@ -47,6 +47,9 @@ CASES = [
     dict(B=24, S=128, d=256, V=1024, n_blocks=120, n_req=60, lo=1, hi=48, R=3),
     # emb_dim the tensor-core kernels do not cover: the engine must route to the SIMT kernels
     dict(B=12, S=64, d=96, V=1000, n_blocks=48, n_req=30, lo=1, hi=30, R=1),
+    # emb_dim 2048 / 4096 (configs[2] / configs[3]): longer K, more feature tiles than SMs allow splits for
+    dict(B=8, S=64, d=2048, V=1024, n_blocks=40, n_req=14, lo=1, hi=40, R=1),
+    dict(B=6, S=64, d=4096, V=1024, n_blocks=28, n_req=9, lo=1, hi=40, R=1),
     # BASELINE configs[4] at one GPU: 8192 rows in one engine (scheduler loops over 1024-thread
     # blocks of rows, 32 GEMM tiles per step, 8192-row attention prefix)
     dict(B=8192, S=64, d=128, V=1024, n_blocks=8192 * 4 + 512, n_req=8192 + 600, lo=1, hi=30, R=1),

@@ -1,6 +1,8 @@
 """tcgen05 3xTF32 GEMM mode (MLI_OPT_GEMM_MODE=0) against the exact-order SIMT mode and the
-reference CUDA kernels.  Tolerance: rel 1e-5 on K/V/q/logits (3xTF32 is ~5e-7; the north_star bound
-is 1e-4), tokens exact on these seeds.  Shapes the tensor-core path does not cover (emb_dim % 128,
+reference CUDA kernels.  Tolerance: rel 1e-5 on K/V/q/logits up to emb_dim 2048 and 2e-5 at emb_dim
+4096 (the products are exact to ~5e-7; what is left is the tensor core's truncating fp32 accumulation
+over chains of up to 1024 products, worst on the reference's all-positive U(0,1] data; the north_star
+bound is 1e-4), tokens exact on these seeds.  Shapes the tensor-core path does not cover (emb_dim % 128,
 n_vocab % 128) must silently use the SIMT kernels and stay bit-exact."""
 import numpy as np
 import pytest
@@ -28,7 +30,7 @@ def tc(ctx):
 
 
 @pytest.mark.parametrize("B,V,d", [(8, 128, 128), (64, 1024, 256), (256, 1024, 1024), (77, 1024, 2048),
-                                   (300, 2048, 512)])
+                                   (300, 2048, 512), (128, 1024, 4096)])   # last: the configs[3] shape
 @pytest.mark.parametrize("dist", ["R", "Z"])
 def test_logits(torch_cuda, tc, ref, B, V, d, dist):
     torch = torch_cuda
@@ -50,12 +52,13 @@ def test_logits(torch_cuda, tc, ref, B, V, d, dist):
         tc.synchronize()
         outs.append((score.cpu().numpy(), dec.cpu().numpy()))
     err = H.rel_err(outs[0][0], outs[1][0])
-    assert err < TOL, f"logits rel err {err:.2e}"
+    assert err < (TOL if d <= 2048 else 2 * TOL), f"logits rel err {err:.2e}"
     assert np.array_equal(outs[0][1], outs[1][1]), "tokens differ between tcgen05 and exact mode"
 
 
 @pytest.mark.parametrize("B,S,d", [(8, 64, 128), (33, 128, 256), (256, 128, 1024), (40, 256, 2048),
-                                   (48, 1024, 128)])   # last: more activation tiles than the grid cap
+                                   (48, 1024, 128),    # more activation tiles than the grid cap
+                                   (24, 64, 4096)])    # emb_dim of BASELINE configs[3]
 @pytest.mark.parametrize("dist", ["R", "Z"])
 @pytest.mark.parametrize("registered", [False, True])
 def test_latest_and_prefill(torch_cuda, tc, ref, B, S, d, dist, registered):
@@ -93,7 +96,8 @@ def test_latest_and_prefill(torch_cuda, tc, ref, B, S, d, dist, registered):
                                          H.p(qr), B, S, d, 0))
     assert np.array_equal(res[1][0], pool_r.cpu().numpy()) and np.array_equal(res[1][1], qr.cpu().numpy())
     e_pool, e_q = H.rel_err(res[0][0], res[1][0]), H.rel_err(res[0][1], res[1][1])
-    assert e_pool < TOL and e_q < TOL, f"K/V rel err {e_pool:.2e}, q rel err {e_q:.2e}"
+    tol = TOL if d <= 2048 else 2 * TOL
+    assert e_pool < tol and e_q < tol, f"K/V rel err {e_pool:.2e}, q rel err {e_q:.2e}"
     # untouched regions (other sub-rows, rows with L == 0, q rows of empty rows) stay bit-identical
     untouched = res[1][0] == case.pool
     assert np.array_equal(res[0][0][untouched], case.pool[untouched])
