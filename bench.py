@@ -484,6 +484,21 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_leg()
             except Exception as e:
                 line["cpu_baseline"] = {"error": str(e)[:200]}
+            try:
+                # in-graph time of every kernel of the step (globaltimer stamps), and the attention
+                # roofline recomputed with the in-graph time instead of the event-bracketed eager launch
+                sys.path.insert(0, str(REPO / "tools"))
+                import step_timeline
+                _, tl = step_timeline.measure(local_rank, ctx.get_option(mli.OPT_PDL))
+                line["step_timeline"] = tl
+                # the last step of the job has no successor stamp: scale the bytes to the steps timed
+                frac_steps = tl["attention_steps"] / max(1, ps.attn_launches)
+                in_graph_gbs = ps.attn_bytes * frac_steps / max(tl["attention_total_us"], 1e-9) / 1e3
+                line["roofline"]["in_graph"] = {
+                    "avg_launch_us": tl["attention_total_us"] / max(1, tl["attention_steps"]),
+                    "achieved": in_graph_gbs, "frac": in_graph_gbs / hbm_peak, "timed_by": tl["timed_by"]}
+            except Exception as e:
+                line["step_timeline"] = {"error": str(e)[:200]}
             if not args.no_large:
                 # the same engine in the HBM-bound regime (not the headline workload): whole jobs at the
                 # BASELINE configs[2] shape and a 32k-context decode at the configs[3] shape

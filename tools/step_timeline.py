@@ -23,16 +23,13 @@ from bench import WORKLOAD  # noqa: E402
 SLOTS = ["sched_step", "encoder", "QKV+prefill GEMM", "decode attention", "logits GEMM", "decoder"]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--pdl", type=int, default=1)
-    ap.add_argument("--out", default="")
-    args = ap.parse_args()
+def measure(device=0, pdl=1):
+    """one traced bench job -> (text report, dict of per-kernel in-graph times)"""
     wl = WORKLOAD
     B, S, d, V = wl["B"], wl["S"], wl["d"], wl["V"]
-    torch.cuda.set_device(0)
-    ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
-    ctx.set_option(mli.OPT_PDL, args.pdl)
+    torch.cuda.set_device(device)
+    ctx = mli.Context(device, torch.cuda.current_stream().cuda_stream)
+    ctx.set_option(mli.OPT_PDL, pdl)
     cap = 4096
     trace = torch.zeros(8 + 8 * cap, dtype=torch.int64, device="cuda")
     trace[1] = cap
@@ -67,7 +64,7 @@ def main():
     for a, k in enumerate(present):
         nxt = tl[:real - 1, present[a + 1]] if a + 1 < len(present) else tl[1:real, 0]
         dur[:, k] = (nxt - tl[:real - 1, k]) / 1e3
-    lines = [f"# In-graph step timeline, bench workload (B={B}, d={d}, S={S}), pdl={args.pdl}",
+    lines = [f"# In-graph step timeline, bench workload (B={B}, d={d}, S={S}), pdl={pdl}",
              "",
              f"{real} engine iterations, {st.generated_tokens} tokens, device job time {st.gpu_ms:.2f} ms "
              f"({1e3 * st.gpu_ms / real:.1f} us / iteration).  Stamp = %globaltimer when the kernel's "
@@ -75,14 +72,19 @@ def main():
              "",
              "| kernel | mean us | median us | p90 us | share |", "|---|---:|---:|---:|---:|"]
     tot = np.nansum(np.nanmean(dur, axis=0))
+    summary = {"iterations": real, "job_ms": float(st.gpu_ms), "us_per_iteration": 1e3 * st.gpu_ms / real,
+               "kernels_mean_us": {}, "timed_by": "%globaltimer stamp of every kernel once its dependencies are satisfied"}
     for k, name in enumerate(SLOTS):
         col = dur[:, k]
         col = col[~np.isnan(col)]
         if not len(col):
             lines.append(f"| {name} | - | - | - | not a separate kernel |")
             continue
+        summary["kernels_mean_us"][name] = float(col.mean())
         lines.append(f"| {name} | {col.mean():.1f} | {np.median(col):.1f} | {np.percentile(col, 90):.1f} | "
                      f"{100 * col.mean() / tot:.1f}% |")
+    summary["attention_total_us"] = float(np.nansum(dur[:, 3]))
+    summary["attention_steps"] = int(np.sum(~np.isnan(dur[:, 3])))
     lines.append(f"\nSum of means {tot:.1f} us per iteration.")
     # the merged GEMM against the rows it saw (active rows padded to 16 + 16 per prefill granule)
     rows = ((n_act + 15) // 16 * 16 + 16 * n_gran)[:real - 1]
@@ -100,12 +102,20 @@ def main():
         if m.any():
             lines.append(f"\nencoder, steps {'with' if has else 'without'} new rows: {int(m.sum())} steps, "
                          f"mean {e[m].mean():.1f} us")
-    text = "\n".join(lines)
+    eng.close()
+    ctx.close()
+    return "\n".join(lines), summary
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    text, _ = measure(0, args.pdl)
     print(text)
     if args.out:
         Path(args.out).write_text(text + "\n")
-    eng.close()
-    ctx.close()
 
 
 if __name__ == "__main__":
