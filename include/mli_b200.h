@@ -51,9 +51,15 @@ typedef enum {
                                          FMA order (bit-exact with the reference's naive kernels) */
     MLI_OPT_ATTN_CHUNK_PAGES = 2, /* KV pages per split of the fused decode attention; 0 = auto */
     MLI_OPT_ATTN_CTAS_PER_SM = 3, /* persistent CTAs per SM for the fused decode attention; 0 = auto */
-    MLI_OPT_PDL = 4               /* 1 (default) = the engine's step graph chains its kernels with
+    MLI_OPT_PDL = 4,              /* 1 (default) = the engine's step graph chains its kernels with
                                          programmatic dependent launch (each kernel's prologue overlaps
                                          the tail of its predecessor); 0 = plain stream order */
+    MLI_OPT_KV_FORMAT = 5         /* 0 (default) = the reference's page float[16][3][d]; 1 = compact page
+                                         (opt-in because the layout is API-visible): a position
+                                         is [inp f32 x d | K bf16 x d | V bf16 x d] = 8*d bytes, i.e. a page
+                                         is 16*2*d floats.  K and V are rounded to bf16 (rel 2^-9) when they
+                                         are written; q, scores, softmax and accumulation stay fp32.  Only the
+                                         tensor-core GEMM mode and the single-launch attention support it. */
 } mli_option;
 
 /* ---- context --------------------------------------------------------------------------- */

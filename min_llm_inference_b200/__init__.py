@@ -6,7 +6,7 @@ Layout:
   capi.py    ctypes binding used by tests/ and bench.py (PyTorch only supplies device memory)
 """
 from .capi import (Context, Engine, EngineCfg, EngineStats, MliError, build_library, load_library,
-                   LIB_PATH, OPT_GEMM_MODE, OPT_ATTN_CHUNK_PAGES, OPT_ATTN_CTAS_PER_SM, OPT_PDL,
+                   LIB_PATH, OPT_GEMM_MODE, OPT_ATTN_CHUNK_PAGES, OPT_ATTN_CTAS_PER_SM, OPT_PDL, OPT_KV_FORMAT,
                    GEMM_TCGEN05, GEMM_SIMT_EXACT, PAGE_BLOCK_SIZE, EOF_TOKEN_ID,
                    EMPTY_ROW_TOKEN_ID, DEFAULT_INIT_NUM_BLOCKS)
 

@@ -19,6 +19,7 @@ OPT_GEMM_MODE = 1
 OPT_ATTN_CHUNK_PAGES = 2
 OPT_ATTN_CTAS_PER_SM = 3
 OPT_PDL = 4
+OPT_KV_FORMAT = 5
 GEMM_TCGEN05 = 0
 GEMM_SIMT_EXACT = 1
 

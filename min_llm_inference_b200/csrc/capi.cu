@@ -185,6 +185,14 @@ int mli_ctx_set_option(mli_ctx* ctx, int option, int value) {
             MLI_REQUIRE(value == 0 || value == 1, "pdl must be 0 or 1");
             ctx->opt_pdl = value;
             return MLI_OK;
+        case MLI_OPT_KV_FORMAT:
+            MLI_REQUIRE(value == 0 || value == 1, "kv format must be 0 (fp32 pages) or 1 (bf16 K/V)");
+            if (value == 1 && !ctx->tc_available) {
+                set_error("the compact KV format needs the tcgen05 GEMM path");
+                return MLI_ERR_UNSUPPORTED;
+            }
+            ctx->kv_bf16 = value;
+            return MLI_OK;
     }
     set_error("unknown option");
     return MLI_ERR_ARG;
@@ -197,6 +205,7 @@ int mli_ctx_get_option(mli_ctx* ctx, int option, int* value) {
         case MLI_OPT_ATTN_CHUNK_PAGES: *value = ctx->attn_chunk_pages; return MLI_OK;
         case MLI_OPT_ATTN_CTAS_PER_SM: *value = ctx->attn_ctas_per_sm; return MLI_OK;
         case MLI_OPT_PDL: *value = ctx->opt_pdl; return MLI_OK;
+        case MLI_OPT_KV_FORMAT: *value = ctx->kv_bf16; return MLI_OK;
     }
     set_error("unknown option");
     return MLI_ERR_ARG;

@@ -41,10 +41,19 @@ void count_launch(int n = 1);
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- page addressing (reference include/utils.h:32-60) -------------------------------------
-// element (row r, position j, sub-row off, column c) =
+// fp32 format (the reference's, API-visible): element (row r, position j, sub-row off, column c) =
 //   page_table[r*W + j/16][(j%16)*3*d + off*d + c]
-__device__ __forceinline__ float* page_row_ptr(float* page, int j, int d, int off) {
-    return page + (size_t)(j & (kPage - 1)) * 3 * d + (size_t)off * d;
+// compact format (MLI_OPT_KV_FORMAT = 1, opt-in): a position is [inp fp32 x d | K bf16 x d | V bf16 x d]
+// = 8*d bytes instead of 12*d; K starts d floats into the position in BOTH formats, K|V stay adjacent.
+__device__ __host__ __forceinline__ size_t page_pos_floats(int d, int kv_bf16) {
+    return kv_bf16 ? 2 * (size_t)d : 3 * (size_t)d;
+}
+// start of sub-row `off` (0 inp, 1 K, 2 V) of position j; for bf16 K / V the result is the byte
+// address of a bf16 row, still typed float*
+__device__ __forceinline__ float* page_row_ptr(float* page, int j, int d, int off, int kv_bf16 = 0) {
+    float* pos = page + (size_t)(j & (kPage - 1)) * page_pos_floats(d, kv_bf16);
+    if (!kv_bf16) return pos + (size_t)off * d;
+    return pos + (off == 0 ? 0 : (off == 1 ? d : d + d / 2));
 }
 
 // ---- PTX wrappers: mbarrier + bulk async copy (TMA, non-tensor form) -------------------------
@@ -225,6 +234,7 @@ struct mli_ctx {
     unsigned long long* trace = nullptr;  // in-graph step timeline buffer (device), else NULL
     void* tc_dbg = nullptr;     // device buffer for GEMM phase stamps (tools/gemm_timing.py), else NULL
     int opt_pdl = 1;            // MLI_OPT_PDL
+    int kv_bf16 = 0;            // MLI_OPT_KV_FORMAT: 1 = compact pages (K, V in bf16)
     bool use_pdl = false;       // launch_kernel() adds programmatic stream serialization (set by the engine)
     bool ws_frozen = false;     // set while a CUDA graph that captured ws pointers is alive
     // when set, the fused decode-attention main kernel is bracketed by these events (profiling)

@@ -112,7 +112,20 @@ struct AttnSeg {
     int pidx;     // partial slot of this segment
 };
 
-template <int NC, int G, bool FUSED>
+// four consecutive columns of a K or V row in the ring: fp32, or bf16 (compact page format) widened
+template <bool KVB>
+__device__ __forceinline__ float4 ld_row4(const float* row, int col) {
+    if constexpr (!KVB) {
+        return reinterpret_cast<const float4*>(row)[col];
+    } else {
+        const uint2 u = reinterpret_cast<const uint2*>(row)[col];
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                           __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    }
+}
+
+// KVB = true: compact page format (MLI_OPT_KV_FORMAT = 1): K and V rows are bf16, half the bytes
+template <int NC, int G, bool FUSED, bool KVB = false>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ page_table,
                         const int* __restrict__ lengths, const int* __restrict__ row_first_g,
@@ -128,7 +141,9 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = S / kPage;
     const int d4 = d >> 2;
-    const int row_floats = 2 * d;            // K row followed by V row
+    const int row_floats = KVB ? d : 2 * d;  // K row followed by V row (as 4-byte words)
+    const int v_off = KVB ? d / 2 : d;       // V row inside a ring row
+    const size_t pos_floats = page_pos_floats(d, KVB ? 1 : 0);
     const int stage_floats = G * row_floats;
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_floats);
@@ -306,7 +321,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                     const float* page = reinterpret_cast<const float*>(
                         __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_page), pg));
                     if (lane < nvalid) {
-                        const float* src = page + (size_t)(j & (kPage - 1)) * 3 * d + d;
+                        const float* src = page + (size_t)(j & (kPage - 1)) * pos_floats + d;   // K starts d floats in
                         bulk_g2s_hint(ring + (size_t)stage * stage_floats + (size_t)lane * row_floats, src,
                                       (uint32_t)row_floats * 4u, &full_bar[stage], kv_policy);
                     }
@@ -522,12 +537,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             for (int g = 0; g < G; ++g) {
                 float s = 0.f;
                 if (g < nvalid) {
-                    const float4* krow = reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats);
+                    const float* krow = sbase + (size_t)g * row_floats;
 #pragma unroll
                     for (int i = 0; i < NC; ++i) {
                         const int col = tid + i * kConsumerThreads;
                         if (col < d4) {
-                            const float4 k = krow[col];
+                            const float4 k = ld_row4<KVB>(krow, col);
                             s = fmaf(qv[i].x, k.x, s);
                             s = fmaf(qv[i].y, k.y, s);
                             s = fmaf(qv[i].z, k.z, s);
@@ -576,13 +591,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             for (int g = 0; g < G; ++g) {
                 const float p = __shfl_sync(0xffffffffu, p_mine, g);
                 if (g < nvalid) {
-                    const float4* vrow =
-                        reinterpret_cast<const float4*>(sbase + (size_t)g * row_floats + d);
+                    const float* vrow = sbase + (size_t)g * row_floats + v_off;
 #pragma unroll
                     for (int i = 0; i < NC; ++i) {
                         const int col = tid + i * kConsumerThreads;
                         if (col < d4) {
-                            const float4 v = vrow[col];
+                            const float4 v = ld_row4<KVB>(vrow, col);
                             acc[i].x = fmaf(p, v.x, acc[i].x);
                             acc[i].y = fmaf(p, v.y, acc[i].y);
                             acc[i].z = fmaf(p, v.z, acc[i].z);
@@ -717,12 +731,14 @@ static int plan_attention(mli_ctx* ctx, int B, int S, int d, bool fused, AttnPla
     }
     p->NC = (d + 1023) / 1024;
     if (p->NC == 3) p->NC = 4;
+    const int kvb = ctx->kv_bf16;
+    const int row_words = kvb ? d : 2 * d;          // 4-byte words of one K|V row in the ring
     int G = 1;
-    while (G < 16 && 2 * G * d <= 4096) G <<= 1;  // G*d <= 4096 floats of K per stage
+    while (G < 16 && G * row_words <= 4096) G <<= 1;  // a stage of at most 32 KB
     // (halving the stage for short contexts was measured: 16 KB stages run at 9 B/cycle per CTA against
     // 12 for 32 KB ones -- the consumers' per-stage barrier / shuffle / exp chain does not shrink)
     p->G = G;
-    const size_t stage_bytes = (size_t)G * 2 * d * 4;
+    const size_t stage_bytes = (size_t)G * row_words * 4;
     int ctas = ctx->attn_ctas_per_sm > 0 ? ctx->attn_ctas_per_sm : 2;
     // the fused kernel also keeps the [B+1] position prefix in shared memory
     const size_t prefix_bytes = fused ? sizeof(int) * ((size_t)B + 1) : 0;
@@ -755,12 +771,12 @@ size_t attention_meta_bytes(int B, int max_items) {
     return sizeof(int) * ((size_t)B + 1 + 2 * (size_t)max_items + 8);
 }
 
-template <int NC, int G, bool FUSED>
+template <int NC, int G, bool FUSED, bool KVB = false>
 static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* const* page_table,
                        const int* lengths, const int* row_first, const int* item_row,
                        const int* item_chunk, float* out, float* part_acc, float* part_ml,
                        float* scores_out, int* row_done, int B, int S, int d) {
-    auto kern = decode_attention_kernel<NC, G, FUSED>;
+    auto kern = decode_attention_kernel<NC, G, FUSED, KVB>;
     const size_t smem = p.smem + (FUSED ? sizeof(int) * ((size_t)B + 1) : 0);
     static size_t configured = 0;  // per instantiation
     if (configured < smem) {
@@ -807,6 +823,25 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
         attn_prep_kernel<<<1, 1024, 0, ctx->stream>>>(lengths, B, p.chunk_pages * kPage, row_first,
                                                        item_row, item_chunk);
         MLI_LAUNCH_CHECK();
+    }
+
+    if (ctx->kv_bf16) {
+        if (!fused) {
+            set_error("compact KV format: the [B,S] probabilities / more than 8192 rows are not supported");
+            return MLI_ERR_UNSUPPORTED;
+        }
+#define MLI_ATTN_BF16(NC_, G_)                                                                       \
+    if (p.NC == NC_ && p.G == G_)                                                                    \
+        return launch_main<NC_, G_, true, true>(p, ctx, q, page_table, lengths, row_first, item_row, \
+                                                item_chunk, out, part_acc, part_ml, softmax_out,     \
+                                                row_done, B, S, d);
+        MLI_ATTN_BF16(1, 16)
+        MLI_ATTN_BF16(1, 8)
+        MLI_ATTN_BF16(2, 4)
+        MLI_ATTN_BF16(4, 2)
+#undef MLI_ATTN_BF16
+        set_error("compact KV format: no attention instantiation for this emb_dim");
+        return MLI_ERR_UNSUPPORTED;
     }
 
 #define MLI_ATTN_CASE(NC_, G_)                                                                       \
@@ -917,11 +952,12 @@ int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_
 }
 
 // algorithmic bytes of one decode-attention launch, from host-side lengths
-double attention_algorithmic_bytes(const int* lengths_host, int B, int d) {
+double attention_algorithmic_bytes(const int* lengths_host, int B, int d, int kv_bf16) {
+    const double kv = kv_bf16 ? 4.0 : 8.0;   // K and V bytes per position and column
     double total = 0;
     for (int r = 0; r < B; ++r) {
         int L = lengths_host[r];
-        if (L > 0) total += 8.0 * d * L + 8.0 * d + 8.0 * ((L + kPage - 1) / kPage) + 4.0;
+        if (L > 0) total += kv * d * L + 8.0 * d + 8.0 * ((L + kPage - 1) / kPage) + 4.0;
     }
     return total;
 }

@@ -551,6 +551,7 @@ struct mli_engine {
     bool submit_timed = false;
     cudaEvent_t ring_ev[4] = {};
     int launches_per_step = 0;     // kernels in the captured step graph
+    int kv_bf16 = 0;               // page format the engine was created with
     cudaEvent_t prof_ev[32] = {};  // profile mode: one event pair per step of a batch (attention)
     cudaEvent_t prof_gev[32] = {}; // the same for the merged GEMM
     int* prof_lengths = nullptr;   // pinned [16][B + 2] (lengths, then the scheduler's two counts), profile mode
@@ -757,7 +758,14 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     e->max_tiles = B * ceil_div(S, kTileM);
     A(dev_alloc(e, &e->tiles, e->max_tiles));
     A(dev_alloc(e, &e->n_tiles, 4));
-    const size_t page_floats = (size_t)kPage * 3 * d;
+    // compact KV format: only with the tensor-core projection (it writes the bf16 rows)
+    if (ctx->kv_bf16 && !(ctx->gemm_mode == 0 && ctx->tc_available && d % 128 == 0 && V % 128 == 0)) {
+        set_error("engine: the compact KV format needs the tcgen05 GEMM mode, emb_dim % 128 == 0 and n_vocab % 128 == 0");
+        mli_engine_destroy(e);
+        return MLI_ERR_UNSUPPORTED;
+    }
+    e->kv_bf16 = ctx->kv_bf16;
+    const size_t page_floats = (size_t)kPage * page_pos_floats(d, ctx->kv_bf16);
     if (cfg->page_pool) {
         e->pool = cfg->page_pool;
     } else {
@@ -833,7 +841,7 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
     MLI_REQUIRE(n_req >= 0 && n_req <= e->cfg.max_requests, "too many requests");
     mli_ctx* ctx = e->ctx;
     StreamScope scope(e);
-    const size_t page_floats = (size_t)kPage * 3 * e->cfg.emb_dim;
+    const size_t page_floats = (size_t)kPage * page_pos_floats(e->cfg.emb_dim, e->kv_bf16);
     const int* d_offs = prompt_offsets;
     const int* d_toks = prompt_tokens;
     MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
@@ -874,6 +882,7 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
 int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     MLI_REQUIRE(e, "null engine");
     mli_ctx* ctx = e->ctx;
+    MLI_REQUIRE(ctx->kv_bf16 == e->kv_bf16, "MLI_OPT_KV_FORMAT was changed after the engine was created");
     StreamScope scope(e);
     int rc;
     const int B = e->cfg.n_batch, d = e->cfg.emb_dim;
@@ -915,7 +924,7 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             MLI_CUDA(cudaStreamSynchronize(ctx->stream));
             for (int k = 0; k < nb; ++k) {
                 const int* slot = e->prof_lengths + (size_t)k * (B + 2);
-                const double bytes = attention_algorithmic_bytes(slot, B, d);
+                const double bytes = attention_algorithmic_bytes(slot, B, d, e->kv_bf16);
                 if (bytes <= 0.0) continue;   // a step past the end of the job: nothing to attend
                 if (ctx->gemm_mode == 0 && ctx->tc_available && d % 128 == 0) {
                     // active rows: K, q, V of one position; granules: K, V of the new rows' earlier

@@ -291,6 +291,10 @@ int launch_gemm(mli_ctx* ctx, const Map& map, const GemmParams& prm, long long w
 int launch_prefill_kv_paged_simt(mli_ctx* ctx, float* const* page_table, const TileDesc* tiles,
                                  const int* n_tiles, int max_tiles, const int* lengths,
                                  const float* wk, const float* wv, int S, int d) {
+    if (ctx->kv_bf16) {
+        set_error("the compact KV format (bf16 K/V) is only implemented for the tcgen05 GEMM mode and emb_dim % 128 == 0");
+        return MLI_ERR_UNSUPPORTED;
+    }
     PrefillPagedMap map{page_table, tiles, n_tiles, lengths, S / kPage, d};
     GemmParams prm{{wk, wv, nullptr}, 2, d, d, d, {1, 1, 1}};
     return launch_gemm<PrefillPagedMap, false>(ctx, map, prm,
@@ -300,6 +304,10 @@ int launch_prefill_kv_paged_simt(mli_ctx* ctx, float* const* page_table, const T
 int launch_qkv_latest_paged_simt(mli_ctx* ctx, float* const* page_table, const int* lengths,
                                  const float* wk, const float* wq, const float* wv, float* q_output,
                                  int B, int S, int d) {
+    if (ctx->kv_bf16) {
+        set_error("the compact KV format (bf16 K/V) is only implemented for the tcgen05 GEMM mode and emb_dim % 128 == 0");
+        return MLI_ERR_UNSUPPORTED;
+    }
     LatestPagedMap map{page_table, lengths, q_output, B, S / kPage, d};
     GemmParams prm{{wk, wq, wv}, 3, d, d, d, {1, 1, 1}};
     return launch_gemm<LatestPagedMap, false>(ctx, map, prm,

@@ -23,6 +23,7 @@
 #include "kernels.h"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <cstdio>
 #include <algorithm>
@@ -158,6 +159,7 @@ struct TcArgs {
     const int* counts;     // [0] = active rows, [1] = granules (device-side)
     const TileDesc* gran;  // STEP: 16-position prefill granules of the new rows
     int use_gran;
+    int kv_bf16;           // compact page format: K and V rows are stored as bf16
     int defer;             // LOGITS: every split rank stores its partial plane (no cross-CTA reduce)
     size_t defer_stride;   // floats between partial planes
     int V, W, B;
@@ -269,9 +271,14 @@ __device__ __forceinline__ RowIO row_io(const TcArgs& args, int n, int n_valid, 
     }
     (void)latest;
     float* page = args.page_table[(size_t)r * args.W + j / kPage];
-    io.src = page_row_ptr(page, j, args.d, 0);
-    io.dst = (mat == 1) ? args.q_out + (size_t)r * args.d + f0
-                        : page_row_ptr(page, j, args.d, mat == 0 ? 1 : 2) + f0;
+    io.src = page_row_ptr(page, j, args.d, 0, args.kv_bf16);
+    if (mat == 1) {
+        io.dst = args.q_out + (size_t)r * args.d + f0;
+    } else {
+        // K / V row of the position; in the compact format it is a bf16 row: f0 elements = f0/2 floats
+        float* row = page_row_ptr(page, j, args.d, mat == 0 ? 1 : 2, args.kv_bf16);
+        io.dst = args.kv_bf16 ? row + f0 / 2 : row + f0;
+    }
     return io;
 }
 
@@ -525,12 +532,24 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const int n_src = own_only ? 1 : split;
             const size_t plane = args.defer ? (size_t)krank * args.defer_stride : 0;
             const int f4 = tid & 31;
+            // compact page format: K and V features leave as bf16 (round to nearest even), q as fp32
+            const bool to_bf16 = args.kv_bf16 && args.mode != TC_LOGITS && mat != 1;
+            auto store_row = [&](float* p, const float4& v) {
+                if (to_bf16) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    reinterpret_cast<uint2*>(p)[f4] = u;
+                } else {
+                    reinterpret_cast<float4*>(p)[f4] = v;
+                }
+            };
             if (own_only) {
                 for (int n = tid >> 5; n < n_eff; n += kTcThreadsV2 / 32) {
                     float* p = dst_tab[n];
                     if (p == nullptr) continue;
-                    reinterpret_cast<float4*>(p + plane)[f4] =
-                        *reinterpret_cast<const float4*>(part + (size_t)n * kBM + f4 * 4);
+                    store_row(p + plane, *reinterpret_cast<const float4*>(part + (size_t)n * kBM + f4 * 4));
                 }
             } else {
                 uint32_t raddr[8];
@@ -547,7 +566,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                     for (int r = 1; r < 8; ++r)
                         if (r < n_src) { sum.x += t[r].x; sum.y += t[r].y; sum.z += t[r].z; sum.w += t[r].w; }
-                    reinterpret_cast<float4*>(p)[f4] = sum;
+                    store_row(p, sum);
                 }
             }
         }
@@ -789,6 +808,7 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     if (nst > kMaxTcStages) nst = kMaxTcStages;
     if (nst < 2) nst = 2;
     args.n_stages = nst;
+    args.kv_bf16 = ctx->kv_bf16;
     args.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
     args.trace = ctx->trace;
     args.trace_slot = (args.mode == TC_LOGITS) ? 4 : 2;

@@ -81,7 +81,7 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
 int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_cache,
                                   const float* v_cache, const int* lengths, float* out,
                                   float* softmax_out, int B, int S, int d);
-double attention_algorithmic_bytes(const int* lengths_host, int B, int d);
+double attention_algorithmic_bytes(const int* lengths_host, int B, int d, int kv_bf16 = 0);
 
 // ---- decoder (src/kernels/decoder.cu:25-91, :128-205) -------------------------------------------
 // score = n_split partial logit planes [n_split][B][V] (1 = plain logits); score_out (optional)

@@ -82,7 +82,7 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
                            const int* __restrict__ req_tok, float* const* __restrict__ page_table,
                            const TileDesc* __restrict__ tiles, const int* __restrict__ n_tiles,
                            const int* __restrict__ lengths, int S, int d, int tile_m,
-                           unsigned long long* trace) {
+                           unsigned long long* trace, int kv_bf16) {
     const int W = S / kPage, d4 = d >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     griddep_wait();
@@ -106,7 +106,7 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
                 const bool on = (m0 + 8 * u < tile_m) && jj[u] < L;
                 tk[u] = on ? toks[jj[u]] : -1;
                 xx[u] = on ? reinterpret_cast<float4*>(
-                                 page_row_ptr(page_table[(size_t)td.row * W + jj[u] / kPage], jj[u], d, 0))
+                                 page_row_ptr(page_table[(size_t)td.row * W + jj[u] / kPage], jj[u], d, 0, kv_bf16))
                            : nullptr;
             }
             for (int c0 = lane; c0 < d4; c0 += 128) {
@@ -147,7 +147,7 @@ int launch_paged_encoder_tiles(mli_ctx* ctx, const float* emb, const float* pos,
     if (grid > max_tiles) grid = max_tiles;
     if (grid < 1) grid = 1;
     return launch_kernel(ctx, paged_encoder_tiles_kernel, dim3(grid), dim3(256), 0, emb, pos, inp, row_req,
-                         req_tok, page_table, tiles, n_tiles, lengths, S, d, tile_m, ctx->trace);
+                         req_tok, page_table, tiles, n_tiles, lengths, S, d, tile_m, ctx->trace, ctx->kv_bf16);
 }
 
 // dense encoder (src/kernels/encoder.cu:56-92); element-wise so any emb_dim works
@@ -191,7 +191,7 @@ decoder_kernel(const float* __restrict__ score, int n_split, size_t split_stride
                int* __restrict__ lengths, float* const* __restrict__ page_table,
                float* __restrict__ inp_embedding, const float* __restrict__ pos,
                const float* __restrict__ emb, int V, int S, int d, int n_dec, int i_dec,
-               unsigned long long* trace) {
+               unsigned long long* trace, int kv_bf16) {
     const int r = blockIdx.x;
     const int tid = threadIdx.x;
     griddep_wait();
@@ -255,7 +255,7 @@ decoder_kernel(const float* __restrict__ score, int n_split, size_t split_stride
     if (stop) return;
     float* x;
     if (PAGED) {
-        x = page_row_ptr(page_table[(size_t)r * (S / kPage) + L / kPage], L, d, 0);
+        x = page_row_ptr(page_table[(size_t)r * (S / kPage) + L / kPage], L, d, 0, kv_bf16);
     } else {
         x = inp_embedding + ((size_t)r * S + L) * d;
     }
@@ -279,7 +279,8 @@ int launch_paged_decoder(mli_ctx* ctx, const float* score, int n_split, float* s
                          int S, int d, int n_dec, int i_dec) {
     return launch_kernel(ctx, decoder_kernel<true>, dim3(B), dim3(256), 0, score, n_split, (size_t)B * V,
                          score_out, decoder_result, lengths,
-                         page_table, static_cast<float*>(nullptr), pos, emb, V, S, d, n_dec, i_dec, ctx->trace);
+                         page_table, static_cast<float*>(nullptr), pos, emb, V, S, d, n_dec, i_dec, ctx->trace,
+                         ctx->kv_bf16);
 }
 
 int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, int* lengths,
@@ -288,7 +289,7 @@ int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, 
     return launch_kernel(ctx, decoder_kernel<false>, dim3(B), dim3(256), 0, score, 1, (size_t)0,
                          static_cast<float*>(nullptr), decoder_result, lengths,
                          static_cast<float* const*>(nullptr), inp_embedding, pos, emb, V, S, d, 1, 0,
-                         static_cast<unsigned long long*>(nullptr));
+                         static_cast<unsigned long long*>(nullptr), 0);
 }
 
 }  // namespace mli

@@ -27,13 +27,16 @@ PRESETS = {
 }
 
 
-def run(name, device=0, reps=2):
+def run(name, device=0, reps=2, kv_bf16=0):
+    """kv_bf16 = 1: the opt-in compact page format (MLI_OPT_KV_FORMAT = 1: K, V stored as bf16)"""
     p = PRESETS[name]
     B, d, S, V = p["B"], p["d"], p["S"], p["V"]
     torch.cuda.set_device(device)
     peak = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
     ctx = mli.Context(device, torch.cuda.current_stream().cuda_stream)
-    page_bytes = 16 * 3 * d * 4
+    if kv_bf16:
+        ctx.set_option(mli.OPT_KV_FORMAT, 1)
+    page_bytes = 16 * (2 if kv_bf16 else 3) * d * 4
     n_blocks = int(p["pool_gb"] * 1e9 // page_bytes)
     w = H.make_weights(1001, d, V, S, "Z")
     offs, toks = H.make_prompts(2002, p["n_req"], p["lo"], p["hi"])
@@ -41,7 +44,7 @@ def run(name, device=0, reps=2):
     ec = mli.EngineCfg(B, S, d, V, n_blocks, 1, 0, p["n_req"], None)
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
     d_offs, d_toks = torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda()
-    out = {"config": name, "n_batch": B, "emb_dim": d, "n_sequence": S, "kv_pool_gb": n_blocks * page_bytes / 1e9,
+    out = {"config": name, "kv_format": "compact (K, V bf16)" if kv_bf16 else "reference (fp32)", "n_batch": B, "emb_dim": d, "n_sequence": S, "kv_pool_gb": n_blocks * page_bytes / 1e9,
            "requests": p["n_req"], "prompt_tokens": int(offs[-1])}
     if p["max_steps"]:
         # step 1 = admission + prefill of every prompt; then a fixed number of decode steps
@@ -61,7 +64,7 @@ def run(name, device=0, reps=2):
                    tokens_per_s=gen / dt, ms_per_step=1e3 * dt / p["max_steps"])
         # rows hold ~prompt + steps tokens: attention bytes per step
         lens = np.diff(offs).astype(np.float64) + p["max_steps"] / 2
-        attn_bytes = float(np.sum(8.0 * d * lens))
+        attn_bytes = float(np.sum((4.0 if kv_bf16 else 8.0) * d * lens))
         out.update(attention_bytes_per_step=attn_bytes,
                    step_floor_ms=1e3 * attn_bytes / (peak * 1e9),
                    whole_step_GBps=attn_bytes / (dt / p["max_steps"]) / 1e9, hbm_peak_GBps=peak)
@@ -85,4 +88,5 @@ def run(name, device=0, reps=2):
 
 
 if __name__ == "__main__":
-    print(json.dumps(run(sys.argv[1] if len(sys.argv) > 1 else "c3")), flush=True)
+    print(json.dumps(run(sys.argv[1] if len(sys.argv) > 1 else "c3",
+                         kv_bf16=1 if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else 0)), flush=True)
