@@ -504,11 +504,12 @@ def main():
                 # BASELINE configs[2] shape and a 32k-context decode at the configs[3] shape
                 sys.path.insert(0, str(REPO / "tools"))
                 eng.close()
-                for key, preset in (("engine_configs2", "c3"), ("engine_configs3", "c4")):
+                for key, preset, kvb in (("engine_configs2", "c3", 0), ("engine_configs3", "c4", 0),
+                                         ("engine_configs2_compact_kv", "c3", 1)):   # opt-in bf16 K/V pages
                     try:
                         import run_config
                         torch.cuda.empty_cache()
-                        line[key] = run_config.run(preset, local_rank, reps=1)
+                        line[key] = run_config.run(preset, local_rank, reps=1, kv_bf16=kvb)
                     except Exception as e:
                         line[key] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
