@@ -166,6 +166,12 @@ __device__ __forceinline__ void griddep_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // optional in-graph step timeline (tools/step_timeline.py): trace[0] = steps seen so far,
 // trace[1] = capacity in steps, trace[8 + 8*step + slot] = globaltimer (ns) at which kernel `slot`
 // of that step had its dependencies satisfied (i.e. its predecessor had completed).  The scheduler

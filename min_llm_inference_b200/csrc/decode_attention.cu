@@ -102,7 +102,21 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // the [B,S] probabilities are requested or B is too large for the shared-memory prefix.
 constexpr int kMaxFusedRows = 8192;
 constexpr int kMaxPend = 32;
-constexpr int kMinDynFair = 256;   // positions per CTA below which all slices are static
+// Slice geometry (macros only so that tools/build_variant.sh can A/B them).  Dynamic slices pay for
+// themselves only on long launches: rows that cross the small dynamic slices are cut into a few dozen
+// partial rows, and the CTAs that finish last merge them serially (measured at B=128, d=4096,
+// S=2048: a 50-65 us tail on a 650 us launch, 6.5 vs 6.8 TB/s all-static; at the configs[3] shape,
+// 9.4 ms per launch, the same tail is noise and the dynamic quarter is worth 3 %).
+#ifndef MLI_ATTN_MIN_DYN
+#define MLI_ATTN_MIN_DYN 4096
+#endif
+#ifndef MLI_ATTN_STATIC_PCT
+#define MLI_ATTN_STATIC_PCT 75
+#endif
+#ifndef MLI_ATTN_DYN_PARTS
+#define MLI_ATTN_DYN_PARTS 3
+#endif
+constexpr int kMinDynFair = MLI_ATTN_MIN_DYN;   // positions per CTA below which all slices are static
 constexpr int kAttnCtrlInts = 16 + kMaxStages + 3 * kMaxPend;
 
 struct AttnSeg {
@@ -125,8 +139,12 @@ __device__ __forceinline__ float4 ld_row4(const float* row, int col) {
 }
 
 // KVB = true: compact page format (MLI_OPT_KV_FORMAT = 1): K and V rows are bf16, half the bytes
+// Two CTAs per SM is what plan_attention() sizes the grid and the rings for, so the register file
+// must allow it (<= 96 registers at 288 threads).  Without the bound the NC = 4 instantiations
+// (emb_dim 4096) took 131 registers, one CTA per SM was resident and the grid ran as two waves
+// (measured at B=128, d=4096, S=2048: 5.0 TB/s, CTA start times spread over 0..610 us; 6.5 TB/s with it).
 template <int NC, int G, bool FUSED, bool KVB = false>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ page_table,
                         const int* __restrict__ lengths, const int* __restrict__ row_first_g,
                         const int* __restrict__ item_row, const int* __restrict__ item_chunk,
@@ -134,10 +152,13 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         float* __restrict__ part_ml, float* __restrict__ scores_out,
                         int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage,
                         long long* __restrict__ dbg, unsigned long long* trace) {
-    // optional phase stamps (tools/attn_timing.py): [cta][8]; slots 0-6 clock64 of consumer thread 0,
-    // slot 7 = segments << 32 | stages this CTA processed
-#define ATTN_STAMP(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+    // optional phase stamps (tools/attn_timing.py): [cta][16]; slots 0-6 clock64 of consumer thread 0,
+    // slot 7 = segments << 32 | stages this CTA processed, slots 8-10 %globaltimer at CTA start / end
+    // of the last segment / CTA end, slot 11 = segments merged << 32 | rows merged
+#define ATTN_STAMP(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#define ATTN_GT(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 16 + (slot)] = (long long)globaltimer_ns(); } while (0)
     ATTN_STAMP(0);
+    ATTN_GT(8);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = S / kPage;
     const int d4 = d >> 2;
@@ -211,10 +232,10 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         // small problems (a fair share of a few dozen positions) are split statically: dynamic
         // slices would be a single pipeline stage each and their claims / merges cost more than
         // the tail they remove
-        qs = (fair * G >= kMinDynFair) ? max(1, fair * 3 / 4) : max(1, fair);
+        qs = (fair * G >= kMinDynFair) ? max(1, fair * MLI_ATTN_STATIC_PCT / 100) : max(1, fair);
         dyn0 = (int)min((long long)P, (long long)grid * qs);
         const int dyn = P - dyn0;
-        qd = max(1, (dyn + 3 * grid - 1) / (3 * grid));
+        qd = max(1, (dyn + MLI_ATTN_DYN_PARTS * grid - 1) / (MLI_ATTN_DYN_PARTS * grid));
         n_slices = grid + (dyn + qd - 1) / qd;
     } else {
         n_items = row_first_g[B];
@@ -378,6 +399,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
             for (int pi = 0; pi < n_pend; ++pi) {
                 if (!pend_flag[pi]) continue;
                 const int r = pend_r[pi], nseg = pend_nseg[pi];
+                if (dbg != nullptr && tid == 0) dbg[(size_t)blockIdx.x * 16 + 11] += ((long long)nseg << 32) | 1;
                 const int start = stage_first[r];
                 const int b_first = slice_of(start);
                 // segment k of the row lives in slice b_first + k: its head slot, except that the
@@ -385,7 +407,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                 auto slot_of = [&](int k) -> size_t {
                     return (size_t)2 * (b_first + k) + ((k == 0 && start != slice_start(b_first)) ? 1 : 0);
                 };
-                if (nseg <= 4) {
+                if (NC < 4 && nseg <= 4) {
                     // common case: every load of the merge is issued before anything is consumed
                     float2 ml[4];
                     float4 pv[4][NC];
@@ -454,11 +476,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                     }
                     Lsum += warp_sum(lw);
                     const int kn = min(32, nseg - k0);
-                    for (int kk = 0; kk < kn; kk += 4) {
-                        float4 pv[4][NC];
-                        float w[4];
+                    constexpr int MU = NC >= 4 ? 2 : 4;   // segments in flight per round (register budget)
+                    for (int kk = 0; kk < kn; kk += MU) {
+                        float4 pv[MU][NC];
+                        float w[MU];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < MU; ++u) {
                             w[u] = __shfl_sync(0xffffffffu, wl, min(kk + u, 31));
                             const size_t sl = slot_of(min(k0 + kk + u, nseg - 1));
 #pragma unroll
@@ -470,7 +493,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < MU; ++u) {
                             if (kk + u < kn) {
 #pragma unroll
                                 for (int i = 0; i < NC; ++i) {
@@ -613,6 +636,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         // ---- segment epilogue ----
         ++n_seg_dbg;
         ATTN_STAMP(5);
+        ATTN_GT(9);
         const int nseg = sg.nseg;
         const size_t pidx = (size_t)sg.pidx;
         if (nseg == 1) {
@@ -663,8 +687,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         }
     }
     ATTN_STAMP(6);
-    if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 8 + 7] = ((long long)n_seg_dbg << 32) | it;
+    ATTN_GT(10);
+    if (dbg != nullptr && threadIdx.x == 0) {
+        dbg[(size_t)blockIdx.x * 16 + 7] = ((long long)n_seg_dbg << 32) | it;
+    }
 #undef ATTN_STAMP
+#undef ATTN_GT
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -119,13 +119,21 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int* s_flag = s_used + B;                                     // [B] bit0 finished, bit1 unoccupied, bits 2.. token count; later: occupied
     int* s_list = s_flag + B;                                     // [B] need list / free rows
     int* s_len = s_list + B;                                      // [B] device lengths as the model kernels will see them
+    // every thread reads the counters itself (one broadcast line) together with its rows' state:
+    // one global round trip, no shared-memory hand-off.  The counters, the row -> request map, the
+    // page counts and the used list are written by this kernel only (the previous iteration's
+    // instance completed long ago), so they are fetched BEFORE the dependency wait; what the decoder
+    // produces (lengths, tokens) is read after it.
+    SchedVars sv = *a.v;
+    for (int r = tid; r < B; r += T) {
+        s_req[r] = a.row_req[r];
+        s_np[r] = a.npages[r];
+        s_flag[r] = 0;
+    }
+    for (int i = tid; i < sv.n_used; i += T) s_used[i] = a.used[i];
     griddep_wait();
     GRIDDEP_TRIGGER_EARLY();
     trace_stamp(a.trace, 0);
-
-    // every thread reads the counters itself (one broadcast line) together with its rows' state:
-    // one global round trip, no shared-memory hand-off
-    SchedVars sv = *a.v;
     if (sv.done) {
         if (tid == 0) {
             a.v->n_new = 0;
@@ -135,13 +143,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         return;
     }
     const bool first = (sv.iter == 0);
-    for (int r = tid; r < B; r += T) {
-        s_req[r] = a.row_req[r];
-        s_np[r] = a.npages[r];
-        s_len[r] = a.lengths[r];
-        s_flag[r] = 0;
-    }
-    for (int i = tid; i < sv.n_used; i += T) s_used[i] = a.used[i];
+    for (int r = tid; r < B; r += T) s_len[r] = a.lengths[r];
     __syncthreads();
     int n_used = sv.n_used;
     int F = sv.f_count, fh = sv.f_head, qh = sv.q_head, qc = sv.q_count;

@@ -23,6 +23,8 @@ def main():
     B, d, S, frac = (int(x) for x in sys.argv[1:5]) if len(sys.argv) >= 5 else (256, 1024, 128, 58)
     torch.cuda.set_device(0)
     ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
+    if os.environ.get("ATTN_KV_BF16"):
+        ctx.set_option(mli.OPT_KV_FORMAT, 1)   # timing only: the pool below keeps the fp32 page size
     if os.environ.get("ATTN_CTAS"):
         ctx.set_option(mli.OPT_ATTN_CTAS_PER_SM, int(os.environ["ATTN_CTAS"]))
     rng = np.random.default_rng(int(os.environ.get("ATTN_SEED", "0")))
@@ -35,7 +37,7 @@ def main():
     out = torch.empty((B, d), device="cuda")
     nbytes = float(np.sum((8.0 * d * L + 8.0 * d + 8.0 * ((L + 15) // 16) + 4.0) * (L > 0)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    stamps = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
+    stamps = torch.zeros((1024, 16), dtype=torch.int64, device="cuda")
 
     def run():
         ctx.call("mli_decode_attention_paged", q, tab, dL, out, None, B, S, d)
@@ -75,7 +77,20 @@ def main():
     st = stamps.cpu().numpy()
     st = st[st[:, 0] != 0]
     smid = st[:, 7]
+    gt = st[:, 8:11].astype(np.float64)
+    merged = st[:, 11]
     st = st[:, :7]
+    # wall-clock picture (globaltimer, common to all SMs): when CTAs start, stop streaming, and end
+    t0 = gt[:, 0].min()
+    rel = (gt - t0) / 1e3
+    print("globaltimer us after the first CTA start, pct 0/10/50/90/100:")
+    for i, nm in enumerate(["CTA start", "last segment done", "CTA end"]):
+        print(f"    {nm:18s}", np.percentile(rel[:, i], [0, 10, 50, 90, 100]).round(1))
+    order = np.argsort(-rel[:, 2])[:10]
+    print("last CTAs to end (cta, start, last-seg, end us; stages, segments; rows merged, segments merged):")
+    for i in order:
+        print(f"    {i:4d} {rel[i, 0]:8.1f} {rel[i, 1]:8.1f} {rel[i, 2]:8.1f}   {int(smid[i] & 0xffffffff):6d} {int(smid[i] >> 32):4d}"
+              f"   {int(merged[i] & 0xffffffff):4d} {int(merged[i] >> 32):5d}")
     have = st[:, 4] != 0
     t_first = (st[have, 4] - st[have, 3]).astype(np.float64)
     t_main = (st[have, 5] - st[have, 4]).astype(np.float64)
