@@ -60,6 +60,17 @@ typedef enum {
                                          is 16*2*d floats.  K and V are rounded to bf16 (rel 2^-9) when they
                                          are written; q, scores, softmax and accumulation stay fp32.  Only the
                                          tensor-core GEMM mode and the single-launch attention support it. */
+    ,
+    MLI_OPT_ATTN_KERNEL = 6       /* consumer design of the single-launch decode attention: 0 (default) =
+                                         auto, 1 = column-split consumers (two CTAs per SM, a position's
+                                         columns spread over 8 warps), 2 = warp-per-position consumers (one
+                                         CTA per SM, 16 warps with private online-softmax states; emb_dim in
+                                         {128, 256, 512, 1024, 2048, 4096}) */
+    ,
+    MLI_OPT_ATTN_MIN_DYN = 7      /* positions per attention CTA (fair share) from which the last quarter of a
+                                         launch is handed out in small dynamic slices; default 4096 (below
+                                         that the merges of the cut rows cost more than the tail they
+                                         remove).  Tests lower it to cover the dynamic path on small inputs */
 } mli_option;
 
 /* ---- context --------------------------------------------------------------------------- */

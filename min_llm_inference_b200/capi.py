@@ -20,6 +20,8 @@ OPT_ATTN_CHUNK_PAGES = 2
 OPT_ATTN_CTAS_PER_SM = 3
 OPT_PDL = 4
 OPT_KV_FORMAT = 5
+OPT_ATTN_KERNEL = 6
+OPT_ATTN_MIN_DYN = 7
 GEMM_TCGEN05 = 0
 GEMM_SIMT_EXACT = 1
 

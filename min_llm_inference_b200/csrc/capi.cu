@@ -193,6 +193,14 @@ int mli_ctx_set_option(mli_ctx* ctx, int option, int value) {
             }
             ctx->kv_bf16 = value;
             return MLI_OK;
+        case MLI_OPT_ATTN_KERNEL:
+            MLI_REQUIRE(value >= 0 && value <= 2, "attention kernel must be 0 (auto), 1 or 2");
+            ctx->attn_kernel = value;
+            return MLI_OK;
+        case MLI_OPT_ATTN_MIN_DYN:
+            MLI_REQUIRE(value >= 1, "the dynamic-slice threshold must be positive");
+            ctx->attn_min_dyn = value;
+            return MLI_OK;
     }
     set_error("unknown option");
     return MLI_ERR_ARG;
@@ -206,6 +214,8 @@ int mli_ctx_get_option(mli_ctx* ctx, int option, int* value) {
         case MLI_OPT_ATTN_CTAS_PER_SM: *value = ctx->attn_ctas_per_sm; return MLI_OK;
         case MLI_OPT_PDL: *value = ctx->opt_pdl; return MLI_OK;
         case MLI_OPT_KV_FORMAT: *value = ctx->kv_bf16; return MLI_OK;
+        case MLI_OPT_ATTN_KERNEL: *value = ctx->attn_kernel; return MLI_OK;
+        case MLI_OPT_ATTN_MIN_DYN: *value = ctx->attn_min_dyn; return MLI_OK;
     }
     set_error("unknown option");
     return MLI_ERR_ARG;

@@ -80,6 +80,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -235,6 +239,8 @@ struct mli_ctx {
     int tc_available = 0;       // tcgen05 GEMM path usable on this device
     int attn_chunk_pages = 0;   // 0 = auto
     int attn_ctas_per_sm = 0;   // 0 = auto
+    int attn_kernel = 0;        // MLI_OPT_ATTN_KERNEL
+    int attn_min_dyn = 4096;    // MLI_OPT_ATTN_MIN_DYN
     void* ws[mli::WS_NUM_SLOTS] = {};
     size_t ws_bytes[mli::WS_NUM_SLOTS] = {};
     unsigned long long* trace = nullptr;  // in-graph step timeline buffer (device), else NULL

@@ -102,21 +102,18 @@ __global__ void attn_prep_kernel(const int* __restrict__ lengths, int B, int chu
 // the [B,S] probabilities are requested or B is too large for the shared-memory prefix.
 constexpr int kMaxFusedRows = 8192;
 constexpr int kMaxPend = 32;
-// Slice geometry (macros only so that tools/build_variant.sh can A/B them).  Dynamic slices pay for
+// Slice geometry.  A launch whose fair share per CTA reaches ctx->attn_min_dyn positions (default
+// 4096, MLI_OPT_ATTN_MIN_DYN) hands the last quarter of the work out dynamically.  Dynamic slices pay for
 // themselves only on long launches: rows that cross the small dynamic slices are cut into a few dozen
 // partial rows, and the CTAs that finish last merge them serially (measured at B=128, d=4096,
 // S=2048: a 50-65 us tail on a 650 us launch, 6.5 vs 6.8 TB/s all-static; at the configs[3] shape,
 // 9.4 ms per launch, the same tail is noise and the dynamic quarter is worth 3 %).
-#ifndef MLI_ATTN_MIN_DYN
-#define MLI_ATTN_MIN_DYN 4096
-#endif
 #ifndef MLI_ATTN_STATIC_PCT
 #define MLI_ATTN_STATIC_PCT 75
 #endif
 #ifndef MLI_ATTN_DYN_PARTS
 #define MLI_ATTN_DYN_PARTS 3
 #endif
-constexpr int kMinDynFair = MLI_ATTN_MIN_DYN;   // positions per CTA below which all slices are static
 constexpr int kAttnCtrlInts = 16 + kMaxStages + 3 * kMaxPend;
 
 struct AttnSeg {
@@ -151,7 +148,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         float* __restrict__ out, float* __restrict__ part_acc,
                         float* __restrict__ part_ml, float* __restrict__ scores_out,
                         int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage,
-                        long long* __restrict__ dbg, unsigned long long* trace) {
+                        int min_dyn, long long* __restrict__ dbg, unsigned long long* trace) {
     // optional phase stamps (tools/attn_timing.py): [cta][16]; slots 0-6 clock64 of consumer thread 0,
     // slot 7 = segments << 32 | stages this CTA processed, slots 8-10 %globaltimer at CTA start / end
     // of the last segment / CTA end, slot 11 = segments merged << 32 | rows merged
@@ -232,7 +229,7 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         // small problems (a fair share of a few dozen positions) are split statically: dynamic
         // slices would be a single pipeline stage each and their claims / merges cost more than
         // the tail they remove
-        qs = (fair * G >= kMinDynFair) ? max(1, fair * MLI_ATTN_STATIC_PCT / 100) : max(1, fair);
+        qs = (fair * G >= min_dyn) ? max(1, fair * MLI_ATTN_STATIC_PCT / 100) : max(1, fair);
         dyn0 = (int)min((long long)P, (long long)grid * qs);
         const int dyn = P - dyn0;
         qd = max(1, (dyn + MLI_ATTN_DYN_PARTS * grid - 1) / (MLI_ATTN_DYN_PARTS * grid));
@@ -814,7 +811,8 @@ static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* c
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
     int rc = launch_kernel(ctx, kern, dim3(p.grid), dim3(kAttnThreads), smem, q, page_table, lengths,
                            row_first, item_row, item_chunk, out, part_acc, part_ml, scores_out, row_done,
-                           B, S, d, p.chunk_pages, p.nstage, reinterpret_cast<long long*>(ctx->tc_dbg), ctx->trace);
+                           B, S, d, p.chunk_pages, p.nstage, ctx->attn_min_dyn,
+                           reinterpret_cast<long long*>(ctx->tc_dbg), ctx->trace);
     if (rc) return rc;
     if (ctx->attn_ev_stop) MLI_CUDA(cudaEventRecord(ctx->attn_ev_stop, ctx->stream));
     return 0;
@@ -833,7 +831,8 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     rc = ws_get(ctx, WS_ATTN_META, attention_meta_bytes(B, p.max_items), &meta);
     if (rc) return rc;
     // partial slots: one per (row, chunk) item (legacy) or two per CTA (fused: slice head / tail)
-    const size_t n_part = std::max((size_t)p.max_items, (size_t)2 * 5 * p.grid);   // fused: <= 4 * grid + grid slices
+    // fused: <= 4 * grid + grid slices, for either kernel's grid
+    const size_t n_part = std::max((size_t)p.max_items, (size_t)2 * 5 * std::max(p.grid, 2 * ctx->num_sms));
     rc = ws_get(ctx, WS_ATTN_PART, sizeof(float) * (n_part * (d + 2) + 8), &part);
     if (rc) return rc;
     rc = ws_get_zeroed(ctx, WS_ATTN_CNT, sizeof(int) * ((size_t)B + 2), &cnt);   // + slice / finished-CTA counters
@@ -846,6 +845,22 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     float* part_acc = part_ml + 2 * n_part;
     // keep part_acc 16-byte aligned
     part_acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(part_acc) + 15) & ~(uintptr_t)15);
+
+    // Which consumer design (MLI_OPT_ATTN_KERNEL, 0 = auto).  Measured on B200 (tools/attn_sweep.py,
+    // profiles/): the warp-per-position kernel is at or above the column-split one on every long
+    // launch -- fp32 pages 7.0-7.3 TB/s either way, bf16 pages 6.5-7.1 vs 5.1-6.1 TB/s, emb_dim 512
+    // 6.5 vs 5.5 TB/s -- but its one CTA per SM pays every row boundary with an SM-wide merge, so on
+    // launches of a few dozen positions per CTA (the configs[1] step: 28.5 vs 25.0 us) the two
+    // interleaved CTAs per SM of the column-split kernel win.  Lengths live on the device, so the
+    // choice goes by what the launch can hold: B * S positions, at least 1024 per SM -> warp-per-position.
+    const bool wp_auto = (long long)B * S >= 1024LL * ctx->num_sms;
+    if (fused && attention_wp_supported(d) && (ctx->attn_kernel == 2 || (ctx->attn_kernel == 0 && wp_auto)))
+        return launch_decode_attention_wp(ctx, q, page_table, lengths, out, part_acc, part_ml, row_done, B,
+                                          S, d, ctx->attn_min_dyn);
+    if (ctx->attn_kernel == 2 && fused) {
+        set_error("decode attention: the warp-per-position kernel has no instantiation for this emb_dim");
+        return MLI_ERR_UNSUPPORTED;
+    }
 
     if (!fused) {
         attn_prep_kernel<<<1, 1024, 0, ctx->stream>>>(lengths, B, p.chunk_pages * kPage, row_first,

@@ -81,6 +81,12 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
 int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_cache,
                                   const float* v_cache, const int* lengths, float* out,
                                   float* softmax_out, int B, int S, int d);
+// warp-per-position variant of the single-launch kernel (decode_attention_wp.cu); workspaces as
+// prepared by launch_decode_attention_paged
+bool attention_wp_supported(int d);
+int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
+                               float* out, float* part_acc, float* part_ml, int* row_done, int B, int S,
+                               int d, int min_dyn);
 double attention_algorithmic_bytes(const int* lengths_host, int B, int d, int kv_bf16 = 0);
 
 // ---- decoder (src/kernels/decoder.cu:25-91, :128-205) -------------------------------------------

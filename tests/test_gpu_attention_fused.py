@@ -1,7 +1,9 @@
 """The production path of the decode attention: ONE fused launch (softmax_out = NULL) -- in-kernel
 position prefix, static + dynamic slices of the flattened position space, partial rows merged by the
 last arriver.  test_gpu_stages.py::test_fused_decode_attention asks for the [B,S] probabilities and
-therefore exercises the three-launch variant; these tests pin the single-launch kernel:
+therefore exercises the three-launch variant; these tests pin the single-launch kernel, in both of
+its consumer designs (MLI_OPT_ATTN_KERNEL: 1 = column-split consumers, 2 = warp-per-position
+consumers, the default where emb_dim allows):
 
   * against the reference's qkt -> softmax -> softmax_v chain (oracle/_ref) at rel 1e-4,
   * on shapes that force every code path: rows cut into many segments (general merge), dynamic tail
@@ -25,6 +27,18 @@ pytestmark = pytest.mark.gpu
 
 def dev(torch, x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+WP_DIMS = (128, 256, 512, 1024, 2048, 4096)   # emb_dim values the warp-per-position kernel covers
+
+
+@pytest.fixture(params=[1, 2], ids=["column-split", "warp-per-position"])
+def attn_kernel(request, ctx):
+    """run the test with each consumer design forced; the context goes back to auto afterwards"""
+    ctx.set_option(mli.OPT_ATTN_KERNEL, request.param)
+    yield request.param
+    ctx.set_option(mli.OPT_ATTN_KERNEL, 0)
+    ctx.set_option(mli.OPT_ATTN_MIN_DYN, 4096)
 
 
 def reference_chain(torch, ref, dq, tab, dL, B, S, d):
@@ -51,7 +65,10 @@ CASES = [
     (7, 512, 2048, "mixed"),
     (3, 1024, 4096, "mixed"),
     (2, 4096, 128, "one_long"),       # a row cut into hundreds of segments: general merge path
-    (64, 2048, 128, "long"),          # fair share >= 256 positions: dynamic tail slices
+    (64, 2048, 128, "long"),          # dynamic tail slices (threshold lowered with MLI_OPT_ATTN_MIN_DYN)
+    (24, 1024, 512, "long"),
+    (40, 512, 2048, "long"),          # warp-per-position: two warps share a position
+    (12, 512, 4096, "long"),          # ... four warps
     (300, 64, 128, "mixed"),          # more rows than the scan block
     (16, 64, 128, "all_empty"),
 ]
@@ -73,8 +90,12 @@ def lengths_for(rng, B, S, spec):
 
 @pytest.mark.parametrize("B,S,d,spec", CASES)
 @pytest.mark.parametrize("dist", ["R", "Z"])
-def test_single_launch_matches_reference(torch_cuda, ctx, ref, B, S, d, spec, dist):
+def test_single_launch_matches_reference(torch_cuda, ctx, ref, attn_kernel, B, S, d, spec, dist):
     torch = torch_cuda
+    if attn_kernel == 2 and d not in WP_DIMS:
+        pytest.skip("no warp-per-position instantiation for this emb_dim (auto uses the column-split kernel)")
+    if spec in ("long", "one_long"):
+        ctx.set_option(mli.OPT_ATTN_MIN_DYN, 64)   # hand the last quarter out dynamically on these small inputs
     rng = np.random.default_rng(900 + B + S + d)
     L = lengths_for(rng, B, S, spec)
     case = H.PagedCase(9, B, S, d, L, dist)
@@ -122,7 +143,7 @@ FULL = [
 
 
 @pytest.mark.parametrize("name,B,S,d,lr", FULL, ids=[f[0] for f in FULL])
-def test_full_size_constant_v_property(torch_cuda, ctx, name, B, S, d, lr):
+def test_full_size_constant_v_property(torch_cuda, ctx, attn_kernel, name, B, S, d, lr):
     """size-independent property: V rows all equal to c  =>  attention output == c for every row
     with L > 0 (the weights sum to one), zeros for empty rows -- at the full BASELINE sizes"""
     torch = torch_cuda
@@ -144,7 +165,7 @@ def test_full_size_constant_v_property(torch_cuda, ctx, name, B, S, d, lr):
 
 
 @pytest.mark.parametrize("name,B,S,d,lr", FULL, ids=[f[0] for f in FULL])
-def test_full_size_rows_against_cpu_oracle(torch_cuda, ctx, name, B, S, d, lr):
+def test_full_size_rows_against_cpu_oracle(torch_cuda, ctx, attn_kernel, name, B, S, d, lr):
     """three rows of the full-size launch (shortest, longest, one more) recomputed by the C oracle"""
     torch = torch_cuda
     rng = np.random.default_rng(11)

@@ -97,8 +97,17 @@ class CompactCase:
         return np.array(inp), np.array(K), np.array(V)
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["column-split", "warp-per-position"])
 @pytest.mark.parametrize("B,S,d", [(8, 64, 128), (40, 128, 1024), (12, 256, 2048), (6, 64, 4096)])
-def test_attention_on_compact_pages(torch_cuda, compact, B, S, d):
+def test_attention_on_compact_pages(torch_cuda, compact, B, S, d, kernel):
+    compact.set_option(mli.OPT_ATTN_KERNEL, kernel)
+    try:
+        _attention_on_compact_pages(torch_cuda, compact, B, S, d)
+    finally:
+        compact.set_option(mli.OPT_ATTN_KERNEL, 0)
+
+
+def _attention_on_compact_pages(torch_cuda, compact, B, S, d):
     torch = torch_cuda
     rng = np.random.default_rng(50 + B + d)
     L = rng.integers(1, S, size=B).astype(np.int32)

@@ -6,6 +6,7 @@ so the configs[2] / configs[3] shapes run in seconds.  Diagnostic tool, not a be
     python tools/attn_sweep.py [--json out.jsonl]
 """
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -20,6 +21,8 @@ import min_llm_inference_b200 as mli  # noqa: E402
 SHAPES = [
     ("bench step (configs[1])", 256, 1024, 128, (1, 126), 0.58),
     ("configs[2]", 1024, 2048, 2048, (64, 2048), 1.0),
+    ("d=512 long", 2048, 512, 2048, (64, 2048), 1.0),
+    ("d=1024 long", 1024, 1024, 2048, (64, 2048), 1.0),
     ("d=2048 mid", 512, 2048, 1024, (1, 1023), 1.0),
     ("d=4096 short", 128, 4096, 2048, (1, 2047), 1.0),
     ("configs[3]", 128, 4096, 32768, (12000, 20000), 1.0),
@@ -85,6 +88,8 @@ def main():
         ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
         if kv_bf16:
             ctx.set_option(mli.OPT_KV_FORMAT, 1)
+        if os.environ.get("ATTN_KERNEL"):
+            ctx.set_option(mli.OPT_ATTN_KERNEL, int(os.environ["ATTN_KERNEL"]))   # 1 column-split, 2 warp-per-position
         for sh in SHAPES:
             r = one(ctx, *sh, kv_bf16)
             r["frac_of_measured_peak"] = r["GBps"] / peak

@@ -25,6 +25,8 @@ def main():
     ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
     if os.environ.get("ATTN_KV_BF16"):
         ctx.set_option(mli.OPT_KV_FORMAT, 1)   # timing only: the pool below keeps the fp32 page size
+    if os.environ.get("ATTN_KERNEL"):
+        ctx.set_option(mli.OPT_ATTN_KERNEL, int(os.environ["ATTN_KERNEL"]))   # 1 column-split, 2 warp-per-position
     if os.environ.get("ATTN_CTAS"):
         ctx.set_option(mli.OPT_ATTN_CTAS_PER_SM, int(os.environ["ATTN_CTAS"]))
     rng = np.random.default_rng(int(os.environ.get("ATTN_SEED", "0")))
