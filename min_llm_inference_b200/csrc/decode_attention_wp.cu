@@ -117,6 +117,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
     int* pend_nseg = pend_r + kWpMaxPend;
     int* pend_flag = pend_nseg + kWpMaxPend;
     int* stage_first = pend_flag + kWpMaxPend;                          // [B + 1]
+    int* len_s = stage_first + B + 1;                                   // [B] the rows' lengths
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -156,7 +157,10 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
         __syncthreads();
         int before = scan_tmp[36];
         for (int w = 0; w < warp; ++w) before += scan_tmp[w];
-        if (r < B) stage_first[r] = before + v - n;
+        if (r < B) {
+            stage_first[r] = before + v - n;
+            len_s[r] = L;
+        }
         __syncthreads();
         if (tid == kWpThreads - 1) scan_tmp[36] = before + v;
         __syncthreads();
@@ -191,7 +195,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
         const int st1 = min(g1 - start, n_st);
         sg.r = lo;
         sg.p0 = (cur - start) * G;
-        sg.p1 = min(st1 * G, lengths[lo]);   // only the row's last stage can be partial
+        sg.p1 = min(st1 * G, len_s[lo]);   // only the row's last stage can be partial
         sg.nseg = slice_of(start + n_st - 1) - slice_of(start) + 1;
         sg.pidx = 2 * slice + (cur == g0 ? 0 : 1);
         cur = start + st1;
@@ -386,16 +390,24 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
             cur = g0;
             if (n_pend + 2 > kWpMaxPend) flush_pending();
         }
-        while (next_seg(cur, sg)) {
+        // The q row of a segment is fetched while the previous segment is being merged, so a row
+        // boundary costs one blocking barrier (deposit -> merge) and no global-memory round trip.
+        float4 qv[NCW];
+        bool have = next_seg(cur, sg);
+        if (have) {
+#pragma unroll
+            for (int i = 0; i < NCW; ++i)
+                qv[i] = reinterpret_cast<const float4*>(q + (size_t)sg.r * d)[cbase + 32 * i];
+        }
+        while (have) {
             const int r = sg.r, p0 = sg.p0, p1 = sg.p1;
-            float4 qv[NCW];
             float4 acc[NCW];
 #pragma unroll
-            for (int i = 0; i < NCW; ++i) {
-                qv[i] = reinterpret_cast<const float4*>(q + (size_t)r * d)[cbase + 32 * i];
-                acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int i = 0; i < NCW; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             float m_run = -INFINITY, l_run = 0.f;
+            // what comes after this segment: looked up now, off the critical path of the row boundary
+            WpSeg sg_nx;
+            const bool have_nx = next_seg(cur, sg_nx);
 
             // positions are dealt round-robin to the PW groups, counted from the segment start; a warp
             // only visits the ring stages that hold one of its positions
@@ -464,6 +476,8 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
             ++n_seg_dbg;
             WP_STAMP(5);
             WP_GT(9);
+            // everybody is done merging the previous segment (long ago, as a rule): scratch is free
+            named_bar_sync(1, kWpConsumerThreads);
             {
                 float* sc = scratch + (size_t)pgrp * d;
 #pragma unroll
@@ -474,16 +488,26 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
                 }
             }
             named_bar_sync(1, kWpConsumerThreads);
-            {
-                float M = -INFINITY;
+            // next segment's q: in flight during the merge
+            if (have_nx) {
 #pragma unroll
-                for (int p = 0; p < PW; ++p) M = fmaxf(M, sml[2 * p]);
+                for (int i = 0; i < NCW; ++i)
+                    qv[i] = reinterpret_cast<const float4*>(q + (size_t)sg_nx.r * d)[cbase + 32 * i];
+            }
+            {
+                // lane p weighs group p (one expf per lane instead of PW per thread)
+                const float2 ml = (lane < PW) ? reinterpret_cast<const float2*>(sml)[lane]
+                                              : make_float2(-INFINITY, 0.f);
+                float M = ml.x;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+                const float wl = expf(ml.x - M);   // groups that got no position: exp(-inf) = 0
                 float w[PW];
                 float Lsum = 0.f;
 #pragma unroll
                 for (int p = 0; p < PW; ++p) {
-                    w[p] = expf(sml[2 * p] - M);   // groups that got no position: exp(-inf) = 0
-                    Lsum += sml[2 * p + 1] * w[p];
+                    w[p] = __shfl_sync(0xffffffffu, wl, p);
+                    Lsum += __shfl_sync(0xffffffffu, ml.y, p) * w[p];   // fixed order: same in every thread
                 }
                 const int nseg = sg.nseg;
                 const size_t pidx = (size_t)sg.pidx;
@@ -510,7 +534,8 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
                     ++n_pend;
                 }
             }
-            named_bar_sync(1, kWpConsumerThreads);   // scratch and sml may be rewritten
+            sg = sg_nx;
+            have = have_nx;
         }
     }   // slices
     GRIDDEP_TRIGGER_LATE();
@@ -534,7 +559,7 @@ size_t wp_smem_bytes(int B, int d, int CW, int G, int nstage, bool kvb) {
     const int PW = wp_consumer_warps(CW) / CW;
     const size_t rowb = kvb ? 4 * (size_t)d : 8 * (size_t)d;
     return (size_t)nstage * G * rowb + sizeof(float) * ((size_t)PW * d + 2 * PW + 2 * PW * CW) +
-           (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + (size_t)B + 1) + 128;
+           (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + 2 * (size_t)B + 1) + 128;
 }
 
 template <int NCW, int CW, bool KVB>
@@ -579,7 +604,7 @@ int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_
     int G = (int)std::max<size_t>(1, (16 * 1024) / rowb);
     if (G > 32) G = 32;
     const size_t fixed = sizeof(float) * ((size_t)PW * d + 2 * PW + 2 * PW * CW) +
-                         (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + (size_t)B + 1) + 128;
+                         (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + 2 * (size_t)B + 1) + 128;
     const size_t budget = 226 * 1024 - fixed;
     int nstage = kWpMaxStages;   // a power of two: the kernel masks instead of dividing
     while (nstage >= 2 && (size_t)nstage * G * rowb > budget) nstage >>= 1;
