@@ -4,6 +4,7 @@
 // device.
 #include "common.cuh"
 #include "kernels.h"
+#include "encoder_body.cuh"
 
 #include <cfloat>
 
@@ -83,59 +84,12 @@ paged_encoder_tiles_kernel(const float* __restrict__ emb, const float* __restric
                            const TileDesc* __restrict__ tiles, const int* __restrict__ n_tiles,
                            const int* __restrict__ lengths, int S, int d, int tile_m,
                            unsigned long long* trace, int kv_bf16) {
-    const int W = S / kPage, d4 = d >> 2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     griddep_wait();
     GRIDDEP_TRIGGER_EARLY();
     trace_stamp(trace, 1);
-    const int nt = *n_tiles;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const TileDesc td = tiles[t];
-        const int L = lengths[td.row];
-        // engine mode: tokens come straight from the device request table (no inp[B,S] copy)
-        const int* toks = row_req ? req_tok + (size_t)row_req[td.row] * S : inp + (size_t)td.row * S;
-        // a warp handles two positions at a time (m and m + 8): both token ids first, then all the
-        // embedding loads of both positions, then the stores -- the kernel is a chain of dependent
-        // (mostly L2-cold) loads, so what matters is how many are in flight together
-        for (int m0 = warp; m0 < tile_m; m0 += 16) {
-            int jj[2], tk[2];
-            float4* xx[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                jj[u] = td.j0 + m0 + 8 * u;
-                const bool on = (m0 + 8 * u < tile_m) && jj[u] < L;
-                tk[u] = on ? toks[jj[u]] : -1;
-                xx[u] = on ? reinterpret_cast<float4*>(
-                                 page_row_ptr(page_table[(size_t)td.row * W + jj[u] / kPage], jj[u], d, 0, kv_bf16))
-                           : nullptr;
-            }
-            for (int c0 = lane; c0 < d4; c0 += 128) {
-                float4 a[2][4], b[2][4];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (tk[u] < 0) continue;
-                    const float4* e = reinterpret_cast<const float4*>(emb + (size_t)tk[u] * d);
-                    const float4* p = reinterpret_cast<const float4*>(pos + (size_t)jj[u] * d);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int c = c0 + 32 * v;
-                        if (c < d4) { a[u][v] = __ldg(e + c); b[u][v] = __ldg(p + c); }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (tk[u] < 0) continue;
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int c = c0 + 32 * v;
-                        if (c < d4)
-                            xx[u][c] = make_float4(a[u][v].x + b[u][v].x, a[u][v].y + b[u][v].y,
-                                                   a[u][v].z + b[u][v].z, a[u][v].w + b[u][v].w);
-                    }
-                }
-            }
-        }
-    }
+    encode_tiles_body(emb, pos, inp, row_req, req_tok, page_table, tiles, *n_tiles, lengths, S, d, tile_m,
+                      kv_bf16, (int)blockIdx.x, (int)gridDim.x, (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5),
+                      (int)(threadIdx.x & 31));
     GRIDDEP_TRIGGER_LATE();
 }
 
