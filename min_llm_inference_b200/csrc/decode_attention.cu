@@ -854,7 +854,7 @@ int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* pa
     // interleaved CTAs per SM of the column-split kernel win.  Lengths live on the device, so the
     // choice goes by what the launch can hold: B * S positions, at least 1024 per SM -> warp-per-position.
     const bool wp_auto = (long long)B * S >= 1024LL * ctx->num_sms;
-    if (fused && attention_wp_supported(d) && (ctx->attn_kernel == 2 || (ctx->attn_kernel == 0 && wp_auto)))
+    if (fused && attention_wp_usable(ctx, B, d) && (ctx->attn_kernel == 2 || (ctx->attn_kernel == 0 && wp_auto)))
         return launch_decode_attention_wp(ctx, q, page_table, lengths, out, part_acc, part_ml, row_done, B,
                                           S, d, ctx->attn_min_dyn);
     if (ctx->attn_kernel == 2 && fused) {

@@ -591,11 +591,10 @@ bool attention_wp_supported(int d) {
 
 int attention_wp_grid(mli_ctx* ctx) { return ctx->num_sms; }
 
-// part_acc / part_ml: two partial slots per slice (<= 5 * grid slices); row_done: [B + 2] zeroed counters
-int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
-                               float* out, float* part_acc, float* part_ml, int* row_done, int B, int S,
-                               int d, int min_dyn) {
-    const bool kvb = ctx->kv_bf16 != 0;
+namespace {
+// ring geometry for a launch: positions per stage and stages (both powers of two); false = the
+// shared memory left after the per-row prefix does not hold two stages
+bool wp_plan(int B, int d, bool kvb, int* G_out, int* nstage_out) {
     const int CW = d <= 1024 ? 1 : d / 1024;
     const int PW = wp_consumer_warps(CW) / CW;
     const size_t rowb = kvb ? 4 * (size_t)d : 8 * (size_t)d;
@@ -605,11 +604,30 @@ int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_
     if (G > 32) G = 32;
     const size_t fixed = sizeof(float) * ((size_t)PW * d + 2 * PW + 2 * PW * CW) +
                          (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + 2 * (size_t)B + 1) + 128;
+    if (fixed >= 226 * 1024) return false;
     const size_t budget = 226 * 1024 - fixed;
     int nstage = kWpMaxStages;   // a power of two: the kernel masks instead of dividing
     while (nstage >= 2 && (size_t)nstage * G * rowb > budget) nstage >>= 1;
-    if (nstage < 2) {
-        set_error("decode attention (warp per position): shared memory too small for this shape");
+    *G_out = G;
+    *nstage_out = nstage;
+    return nstage >= 2;
+}
+}  // namespace
+
+// does the kernel cover this launch (instantiated emb_dim, room for the ring)?
+bool attention_wp_usable(mli_ctx* ctx, int B, int d) {
+    int G, nstage;
+    return attention_wp_supported(d) && wp_plan(B, d, ctx->kv_bf16 != 0, &G, &nstage);
+}
+
+// part_acc / part_ml: two partial slots per slice (<= 5 * grid slices); row_done: [B + 2] zeroed counters
+int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
+                               float* out, float* part_acc, float* part_ml, int* row_done, int B, int S,
+                               int d, int min_dyn) {
+    const bool kvb = ctx->kv_bf16 != 0;
+    int G = 1, nstage = 0;
+    if (!attention_wp_supported(d) || !wp_plan(B, d, kvb, &G, &nstage)) {
+        set_error("decode attention (warp per position): shape not covered (emb_dim / shared memory)");
         return MLI_ERR_UNSUPPORTED;
     }
     const int grid = attention_wp_grid(ctx);

@@ -84,6 +84,7 @@ int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_
 // warp-per-position variant of the single-launch kernel (decode_attention_wp.cu); workspaces as
 // prepared by launch_decode_attention_paged
 bool attention_wp_supported(int d);
+bool attention_wp_usable(mli_ctx* ctx, int B, int d);
 int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
                                float* out, float* part_acc, float* part_ml, int* row_done, int B, int S,
                                int d, int min_dyn);
