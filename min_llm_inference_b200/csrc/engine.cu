@@ -131,6 +131,17 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         s_flag[r] = 0;
     }
     for (int i = tid; i < sv.n_used; i += T) s_used[i] = a.used[i];
+    // likewise the head of the free ring (window entry j = ring[f_head + j]; pages freed later in
+    // this step are forwarded into the window by the code that frees them) and the head of the
+    // queue with the request lengths: what the admission phase would otherwise fetch through two
+    // dependent round trips at the very end of the kernel
+    const int F0 = sv.f_count;
+    for (int j = tid; j < min(F0, n_fq); j += T) fq[j] = a.free_ring[(sv.f_head + j) % a.n_blocks];
+    int pq_id = -1, pq_len = 0;
+    if (tid < sv.q_count) {
+        pq_id = a.queue[(sv.q_head + tid) % sv.q_cap];
+        pq_len = a.req_cnt[pq_id];
+    }
     griddep_wait();
     GRIDDEP_TRIGGER_EARLY();
     trace_stamp(a.trace, 0);
@@ -213,9 +224,12 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 const int kpos = block_scan_excl(keep, &totk, s_warp, scan_phase);
                 // every read of s_used[] in this chunk is done (the scans contain barriers)
                 if (rel) {
-                    const int o = fh + F + freed + ppos;
-                    for (int t = 0; t < np; ++t)
-                        a.free_ring[(o + t) % nb] = a.page_table[(size_t)row * W + t];
+                    const int wj = F + freed + ppos;   // window index (the ring head does not move here)
+                    for (int t = 0; t < np; ++t) {
+                        float* pg = a.page_table[(size_t)row * W + t];
+                        a.free_ring[(fh + wj + t) % nb] = pg;
+                        if (wj + t < n_fq) fq[wj + t] = pg;
+                    }
                     s_np[row] = 0;
                 }
                 if (keep) s_used[kept + kpos] = row;
@@ -245,8 +259,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             }
             // window of the free ring the growth loop may consume: entry j = ring[fh + j]
             const int fh0 = fh;   // entry j of the window is ring[fh0 + j]
-            const int n_win = min(min(F, m), n_fq);
-            for (int j = tid; j < n_win; j += T) fq[j] = a.free_ring[(fh0 + j) % nb];
+            // (its first min(F, n_fq) entries are in shared memory already: fetched before the
+            // dependency wait, or forwarded by phase 2)
             __syncthreads();
             if (F >= m) {
                 // every row that needs a page finds one: no pre-emption can happen and the pages are
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             n_free_rows += tot;
         }
         const int n_cand = min(n_free_rows, qc);
+        const int w_used = (fh - sv.f_head + nb) % nb;   // window entries the growth phase consumed
         // candidate j takes queue item j; admitted iff cumulative page need <= F (a prefix)
         if (tid == 0) s_carry[0] = 0;
         __syncthreads();
@@ -365,8 +380,13 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             const int j = base + tid;
             int id = -1, len = 0, need = 0;
             if (j < n_cand) {
-                id = a.queue[(qh + j) % q_cap];
-                len = a.req_cnt[id];
+                if (base == 0 && qh == sv.q_head && tid < sv.q_count) {
+                    id = pq_id;   // nothing was pushed to the front of the queue in this step
+                    len = pq_len;
+                } else {
+                    id = a.queue[(qh + j) % q_cap];
+                    len = a.req_cnt[id];
+                }
                 need = max((len + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
             }
             int totn;
@@ -377,8 +397,11 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             if (admit) {
                 const int row = s_list[j];
                 const int np = min(need, W);
-                for (int t = 0; t < np; ++t)
-                    a.page_table[(size_t)row * W + t] = a.free_ring[(fh + before + t) % nb];
+                for (int t = 0; t < np; ++t) {
+                    const int wi = w_used + before + t;   // window entry = ring[f_head at entry + wi]
+                    a.page_table[(size_t)row * W + t] =
+                        (wi < n_fq) ? fq[wi] : a.free_ring[(fh + before + t) % nb];
+                }
                 s_np[row] = np;
                 s_len[row] = len;
                 a.lengths[row] = len;
