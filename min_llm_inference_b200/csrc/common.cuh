@@ -179,7 +179,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // optional in-graph step timeline (tools/step_timeline.py): trace[0] = steps seen so far,
 // trace[1] = capacity in steps, trace[8 + 8*step + slot] = globaltimer (ns) at which kernel `slot`
 // of that step had its dependencies satisfied (i.e. its predecessor had completed).  The scheduler
-// (slot 0) opens a new step.
+// (slot 0) opens a new step.  trace[2] != 0 (tools/sched_timing.py): the scheduler also records 16
+// phase stamps per step after the step table, at trace[8 + 8*capacity + 16*step + phase].
 __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
     if (trace == nullptr) return;
     if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) != 0) return;

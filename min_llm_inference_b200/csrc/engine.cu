@@ -119,6 +119,13 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int* s_flag = s_used + B;                                     // [B] bit0 finished, bit1 unoccupied, bits 2.. token count; later: occupied
     int* s_list = s_flag + B;                                     // [B] need list / free rows
     int* s_len = s_list + B;                                      // [B] device lengths as the model kernels will see them
+    // optional phase stamps (tools/sched_timing.py): trace[2] != 0 -> 16 %globaltimer slots per step after
+    // the step table
+    unsigned long long* ph = nullptr;
+    if (tid == 0 && a.trace != nullptr && a.trace[2] != 0 && a.trace[0] < a.trace[1])
+        ph = a.trace + 8 + 8 * a.trace[1] + 16 * a.trace[0];
+#define SCHED_PH(k) do { if (ph != nullptr) ph[k] = globaltimer_ns(); } while (0)
+    SCHED_PH(0);
     // every thread reads the counters itself (one broadcast line) together with its rows' state:
     // one global round trip, no shared-memory hand-off.  The counters, the row -> request map, the
     // page counts and the used list are written by this kernel only (the previous iteration's
@@ -142,7 +149,9 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         pq_id = a.queue[(sv.q_head + tid) % sv.q_cap];
         pq_len = a.req_cnt[pq_id];
     }
+    SCHED_PH(1);
     griddep_wait();
+    SCHED_PH(2);
     GRIDDEP_TRIGGER_EARLY();
     trace_stamp(a.trace, 0);
     if (sv.done) {
@@ -156,6 +165,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     const bool first = (sv.iter == 0);
     for (int r = tid; r < B; r += T) s_len[r] = a.lengths[r];
     __syncthreads();
+    SCHED_PH(3);
     int n_used = sv.n_used;
     int F = sv.f_count, fh = sv.f_head, qh = sv.q_head, qc = sv.q_count;
     const int q_cap = sv.q_cap, nb = a.n_blocks;
@@ -207,6 +217,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         }
         if (tid == 0) a.v->n_fin = n_fin;
 
+        SCHED_PH(4);
         // ================= phase 2: free rows in finished_indices (paged_item_storage.cpp:20-32) =====
         {
             int kept = 0, freed = 0;
@@ -242,6 +253,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         }
         __syncthreads();   // ring writes of phase 2 are read back below
 
+        SCHED_PH(5);
         // ================= phase 3: grow / pre-empt (paged_item_storage.cpp:36-59) ===================
         {
             int m = 0;
@@ -353,6 +365,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         }
     }
 
+    SCHED_PH(6);
     // ================= phase 4: insert_new_items (paged_item_storage.cpp:62-122) =====================
     int k_adm = 0;
     {
@@ -439,6 +452,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         __syncthreads();
     }
 
+    SCHED_PH(7);
     GRIDDEP_TRIGGER_LATE();
     // ---- write the mirrors back ----
     for (int r = tid; r < B; r += T) {
@@ -476,6 +490,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         n_gran += tot;
     }
 
+    SCHED_PH(8);
     if (tid == 0) {
         SchedVars* v = a.v;
         v->f_head = fh;
@@ -502,6 +517,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             v->steps = sv.steps + 1;
         }
     }
+    SCHED_PH(9);
+#undef SCHED_PH
 }
 
 __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats, int max_req) {
