@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             if (fr) s_list[n_free_rows + pos] = r;
             n_free_rows += tot;
         }
-        const int n_cand = min(n_free_rows, qc);
+        // an admission takes at least MLI_DEFAULT_INIT_NUM_BLOCKS pages (:86-88): with fewer free pages
+        // nobody gets in and the candidate scans (four block barriers) are skipped
+        const int n_cand = (F >= MLI_DEFAULT_INIT_NUM_BLOCKS) ? min(n_free_rows, qc) : 0;
         const int w_used = (fh - sv.f_head + nb) % nb;   // window entries the growth phase consumed
         // candidate j takes queue item j; admitted iff cumulative page need <= F (a prefix)
         if (tid == 0) s_carry[0] = 0;
