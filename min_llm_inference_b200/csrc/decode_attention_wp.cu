@@ -9,12 +9,19 @@
 //     run in lock step, one pipeline stage at a time.  That chain is ~500 + 300 * (d / 1024) cycles
 //     per position (tools/attn_timing.py): hidden behind HBM for fp32 pages, but the limit for the
 //     compact bf16 page format (half the bytes per position) and for emb_dim < 1024.
-//   * here ONE CTA per SM runs 16 consumer warps, and a position belongs to one warp (emb_dim <=
-//     1024) or to CW = emb_dim / 1024 warps that split its columns.  Every warp (group) keeps its
+//   * here ONE CTA per SM runs 16 warps (a producer and 15 / 14 / 12 consumers), and a position
+//     belongs to one warp (emb_dim <= 1024) or to CW = emb_dim / 1024 warps that split its columns
+//     (a named barrier of those CW warps per position).  Every warp (group) keeps its
 //     own online-softmax state (m, l, acc) over the positions it was dealt, so there is no CTA-wide
 //     synchronisation inside a row segment at all: positions of a pipeline stage are processed
 //     concurrently by different warps, and warps drift apart freely.  The per-group states are merged
 //     through shared memory once per segment.
+//
+//   * a warp visits only the ring stages that hold its positions (see wp_wait_issued), slice ids
+//     travel in a small box of their own, and at a row boundary the next row's q is fetched while
+//     the groups' states are merged.
+// Chosen by launch_decode_attention_paged for launches that can hold >= 1024 positions per SM
+// (measured against the column-split kernel in profiles/r1_attn_sweep.jsonl).
 //
 // Scale is dot / sqrtf(d) and the exponent is expf, as in the reference.
 #include "common.cuh"
