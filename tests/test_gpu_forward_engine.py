@@ -141,6 +141,27 @@ def test_engine_vs_reference_dense_engine(torch_cuda, ctx, ref, case, dist):
         assert np.array_equal(mine[i], theirs[i]), f"request {i}: tokens differ from the reference"
 
 
+@pytest.mark.parametrize("case", [c for c in ENGINE_CASES if c["d"] in (128, 256)],
+                         ids=lambda c: f"B{c['B']}-d{c['d']}")
+@pytest.mark.parametrize("dist", ["R", "Z"])
+def test_engine_with_warp_per_position_attention(torch_cuda, ctx, ref, case, dist):
+    """P2 again with the attention's other consumer design forced (MLI_OPT_ATTN_KERNEL = 2; auto picks it
+    only for long launches): tokens of every request equal the reference's non-paged engine"""
+    torch = torch_cuda
+    ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+    ctx.set_option(mli.OPT_ATTN_KERNEL, 2)
+    try:
+        w = H.make_weights(31, case["d"], case["V"], case["S"], dist)
+        offs, toks = H.make_prompts(33, case["n_req"], case["lo"], case["hi"])
+        mine, order, st = run_mli_engine(ctx, torch, case, w, offs, toks, compat=0)
+    finally:
+        ctx.set_option(mli.OPT_ATTN_KERNEL, 0)
+    theirs, _, _ = run_ref_engine(ref, "dense", case, w, offs, toks)
+    assert st.n_finished == case["n_req"] == len(theirs)
+    bad = [i for i in range(case["n_req"]) if not np.array_equal(mine[i], theirs[i])]
+    assert not bad, f"requests {bad}: tokens differ from the reference"
+
+
 @pytest.mark.parametrize("case", ENGINE_CASES)
 @pytest.mark.parametrize("dist", ["R", "Z"])
 @pytest.mark.parametrize("variant", [0, 1])
