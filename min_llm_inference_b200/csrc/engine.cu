@@ -992,7 +992,13 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
         // first is chained to the previous decoder with programmatic dependent launch; steps past
         // the end of the job find an empty engine and cost a few microseconds); bounded runs replay
         // a one-step graph.
-        constexpr int kStepsPerGraph = 4;
+#ifndef MLI_STEPS_PER_GRAPH
+#define MLI_STEPS_PER_GRAPH 4
+#endif
+#ifndef MLI_GRAPHS_AHEAD
+#define MLI_GRAPHS_AHEAD 2
+#endif
+        constexpr int kStepsPerGraph = MLI_STEPS_PER_GRAPH;
         const int per = (max_steps > 0) ? 1 : kStepsPerGraph;
         cudaGraphExec_t& gexec = (per == 1) ? e->graph_exec : e->graphn_exec;
         cudaGraph_t& g = (per == 1) ? e->graph : e->graphn;
@@ -1013,7 +1019,7 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             MLI_CUDA(cudaGraphInstantiate(&gexec, g, 0));
             ctx->ws_frozen = true;
         }
-        const int kAhead = (per == 1) ? 4 : 2;   // graphs in flight before the host looks at `done`
+        const int kAhead = (per == 1) ? 4 : MLI_GRAPHS_AHEAD;   // graphs in flight before the host looks at `done`
         for (;; it += per) {
             if (max_steps > 0 && it >= max_steps) break;
             const int slot = (int)((it / per) % kAhead);
