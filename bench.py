@@ -143,8 +143,8 @@ def reference_arm(args, rank, world):
     sample = (f"first {sample_rows} of {wl['n_req']} requests on {sample_rows} rows, prefill + "
               f"{sample_iters} engine iterations per step, same d/S/V/prompt distribution")
     times, gens = [], []
-    if H.ref_available():
-        import torch  # the reference's host tensors are cudaHostAlloc'd: needs a CUDA context
+    import torch  # the reference's host tensors are cudaHostAlloc'd: it needs a CUDA context
+    if H.ref_available() and torch.cuda.is_available():
         torch.cuda.init()
         ref = H.load_ref()
         kind, cores = "reference", 1
