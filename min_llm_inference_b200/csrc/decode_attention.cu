@@ -156,6 +156,11 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
 #define ATTN_GT(slot) do { if (dbg != nullptr && threadIdx.x == 0) dbg[(size_t)blockIdx.x * 16 + (slot)] = (long long)globaltimer_ns(); } while (0)
     ATTN_STAMP(0);
     ATTN_GT(8);
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[(size_t)blockIdx.x * 16 + 12] = (long long)smid;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = S / kPage;
     const int d4 = d >> 2;

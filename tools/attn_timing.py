@@ -81,6 +81,7 @@ def main():
     smid = st[:, 7]
     gt = st[:, 8:11].astype(np.float64)
     merged = st[:, 11]
+    sm_of_cta = st[:, 12]
     st = st[:, :7]
     # wall-clock picture (globaltimer, common to all SMs): when CTAs start, stop streaming, and end
     t0 = gt[:, 0].min()
@@ -113,6 +114,13 @@ def main():
     print("slowest main loops (stages, segments, cycles):", [(int(nstage[i]), int(nseg[i]), int(t_main[i])) for i in order])
     order = np.argsort(t_main)[:8]
     print("fastest main loops (stages, segments, cycles):", [(int(nstage[i]), int(nseg[i]), int(t_main[i])) for i in order])
+    # which SMs are slow?  (ATTN_SM_DUMP=file: per-SM mean main-loop cycles, to compare runs / seeds)
+    if os.environ.get("ATTN_SM_DUMP"):
+        sm = sm_of_cta[have]
+        per_sm = np.array([t_main[sm == i].mean() if np.any(sm == i) else np.nan for i in range(int(sm.max()) + 1)])
+        np.save(os.environ["ATTN_SM_DUMP"], per_sm)
+        print("per-SM mean main loop: min/median/max", np.nanmin(per_sm).round(), np.nanmedian(per_sm).round(),
+              np.nanmax(per_sm).round(), " slowest SMs:", np.argsort(-np.nan_to_num(per_sm))[:12].tolist())
     dl = np.diff(st, axis=1).astype(np.float64)
     print(f"{len(st)} CTAs stamped (cold L2)")
     for i, nm in enumerate(NAMES):
