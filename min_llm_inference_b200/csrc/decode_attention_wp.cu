@@ -193,10 +193,17 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
     // work iterator, identical in the producer and the consumers; `cur` is a global stage index
     auto next_seg = [&](int& cur, WpSeg& sg) -> bool {
         if (cur >= g1) return false;
-        int lo = 0, hi = B;   // largest r with stage_first[r] <= cur (empty rows share a start: skipped)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (stage_first[mid] <= cur) lo = mid; else hi = mid;
+        // largest r with stage_first[r] <= cur (empty rows share a start: skipped), by a warp-cooperative
+        // 32-ary search: every lane probes one candidate per round (all lanes call next_seg together)
+        int lo = 0;
+        for (int n = B; n > 1;) {
+            const int step = (n + 31) >> 5;
+            const int idx = lo + lane * step;
+            const bool le = (idx < lo + n) && (stage_first[idx] <= cur);
+            const int k = 31 - __clz(__ballot_sync(0xffffffffu, le));   // lane 0 always qualifies
+            const int end = lo + n;
+            lo += k * step;
+            n = min(step, end - lo);
         }
         const int start = stage_first[lo], n_st = stage_first[lo + 1] - start;
         const int st1 = min(g1 - start, n_st);

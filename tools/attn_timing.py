@@ -34,6 +34,16 @@ def main():
     L[rng.random(B) > frac / 100.0] = 0          # ~58 % of rows active, as in the bench job
     case = H.PagedCase(1, B, S, d, L, "Z")
     pool, tab = case.device(torch)
+    if os.environ.get("ATTN_ALIAS_MB"):
+        # experiment: fold the page table onto the first N MB of the pool (same logical work, few
+        # distinct 2 MB translations) -- separates address-translation effects from the rest
+        page_bytes = 16 * 3 * d * 4
+        n_alias = max(1, int(float(os.environ["ATTN_ALIAS_MB"]) * 2**20) // page_bytes)
+        base = pool.data_ptr()
+        live = tab != 0
+        ids = (tab - base) // page_bytes
+        tab = torch.where(live, base + (ids % n_alias) * page_bytes, tab)
+        print(f"page table folded onto {n_alias} pages ({n_alias * page_bytes / 2**20:.1f} MB)")
     dL = torch.from_numpy(L).cuda()
     q = (torch.rand((B, d), device="cuda") - 0.5) * 0.1
     out = torch.empty((B, d), device="cuda")
