@@ -114,7 +114,7 @@ constexpr int kMaxPend = 32;
 #ifndef MLI_ATTN_DYN_PARTS
 #define MLI_ATTN_DYN_PARTS 3
 #endif
-constexpr int kAttnCtrlInts = 16 + kMaxStages + 3 * kMaxPend;
+constexpr int kAttnCtrlInts = 32 + kMaxStages + 3 * kMaxPend;
 
 struct AttnSeg {
     int r;        // batch row
@@ -172,8 +172,8 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_floats);
     uint64_t* empty_bar = full_bar + kMaxStages;
     float* red = reinterpret_cast<float*>(empty_bar + kMaxStages);  // [2][kConsumerWarps][G]
-    int* scan_tmp = reinterpret_cast<int*>(red + 2 * kConsumerWarps * G);   // [16]: warp totals, carry
-    int* stage_meta = scan_tmp + 16;                                         // [kMaxStages] slice opened by a stage
+    int* scan_tmp = reinterpret_cast<int*>(red + 2 * kConsumerWarps * G);   // [2][16]: warp totals of the prefix scan
+    int* stage_meta = scan_tmp + 32;                                         // [kMaxStages] slice opened by a stage
     int* pend_r = stage_meta + kMaxStages;                                   // [kMaxPend] partial rows to merge
     int* pend_nseg = pend_r + kMaxPend;
     int* pend_flag = pend_nseg + kMaxPend;
@@ -205,10 +205,11 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     // qd stages that CTAs claim from a global counter as they run dry.
     int qs = 1, qd = 1, dyn0 = 0, n_slices = 0, P = 0;
     if constexpr (FUSED) {
-        // exclusive prefix of the rows' stage counts, kAttnThreads rows at a time
-        if (tid == 0) scan_tmp[12] = 0;
-        __syncthreads();
-        for (int base = 0; base < B; base += kAttnThreads) {
+        // exclusive prefix of the rows' stage counts, kAttnThreads rows at a time: one barrier per
+        // round (the warp totals are double-buffered, the running total lives in a register of every
+        // thread) and one at the end
+        int carry = 0;
+        for (int base = 0, round = 0; base < B; base += kAttnThreads, ++round) {
             const int r = base + tid;
             const int n = (r < B) ? (lengths[r] + G - 1) / G : 0;
             int v = n;
@@ -217,16 +218,20 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                 const int t = __shfl_up_sync(0xffffffffu, v, o);
                 if (lane >= o) v += t;
             }
-            if (lane == 31) scan_tmp[warp] = v;
+            int* tot = scan_tmp + 16 * (round & 1);
+            if (lane == 31) tot[warp] = v;
             __syncthreads();
-            int before = scan_tmp[12];
-            for (int w = 0; w < warp; ++w) before += scan_tmp[w];
+            int before = carry, all = 0;
+#pragma unroll
+            for (int w = 0; w < kAttnThreads / 32; ++w) {
+                const int t = tot[w];
+                all += t;
+                if (w < warp) before += t;
+            }
             if (r < B) stage_first[r] = before + v - n;
-            __syncthreads();
-            if (tid == kAttnThreads - 1) scan_tmp[12] = before + v;
-            __syncthreads();
+            carry += all;
         }
-        P = scan_tmp[12];
+        P = carry;
         if (tid == 0) stage_first[B] = P;
         __syncthreads();
         const int grid = (int)gridDim.x;

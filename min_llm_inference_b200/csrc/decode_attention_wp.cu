@@ -147,10 +147,10 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
     trace_stamp(trace, 3);
     WP_STAMP(1);
 
-    // ---- prefix of the rows' stage counts (a stage = G positions of one row) ----
-    if (tid == 0) scan_tmp[36] = 0;
-    __syncthreads();
-    for (int base = 0; base < B; base += kWpThreads) {
+    // ---- prefix of the rows' stage counts (a stage = G positions of one row): one barrier per round
+    // (double-buffered warp totals, running total in a register of every thread) and one at the end ----
+    int P = 0;
+    for (int base = 0, round = 0; base < B; base += kWpThreads, ++round) {
         const int r = base + tid;
         const int L = (r < B) ? lengths[r] : 0;
         const int n = (L + G - 1) / G;
@@ -160,19 +160,22 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
             const int t = __shfl_up_sync(0xffffffffu, v, o);
             if (lane >= o) v += t;
         }
-        if (lane == 31) scan_tmp[warp] = v;
+        int* tot = scan_tmp + 16 * (round & 1);
+        if (lane == 31) tot[warp] = v;
         __syncthreads();
-        int before = scan_tmp[36];
-        for (int w = 0; w < warp; ++w) before += scan_tmp[w];
+        int before = P, all = 0;
+#pragma unroll
+        for (int w = 0; w < kWpThreads / 32; ++w) {
+            const int t = tot[w];
+            all += t;
+            if (w < warp) before += t;
+        }
         if (r < B) {
             stage_first[r] = before + v - n;
             len_s[r] = L;
         }
-        __syncthreads();
-        if (tid == kWpThreads - 1) scan_tmp[36] = before + v;
-        __syncthreads();
+        P += all;
     }
-    const int P = scan_tmp[36];
     if (tid == 0) stage_first[B] = P;
     __syncthreads();
     // slices of the flattened stage space: [0, grid) static, then dynamic ones (claimed with an
