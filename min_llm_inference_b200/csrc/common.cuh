@@ -242,6 +242,7 @@ struct mli_ctx {
     int attn_ctas_per_sm = 0;   // 0 = auto
     int attn_kernel = 0;        // MLI_OPT_ATTN_KERNEL
     int attn_min_dyn = 4096;    // MLI_OPT_ATTN_MIN_DYN
+    int attn_lengths_final = 0; // set by the engine around its attention launch: lengths[] may be read ahead of the dependency wait
     void* ws[mli::WS_NUM_SLOTS] = {};
     size_t ws_bytes[mli::WS_NUM_SLOTS] = {};
     unsigned long long* trace = nullptr;  // in-graph step timeline buffer (device), else NULL

@@ -148,7 +148,8 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
                         float* __restrict__ out, float* __restrict__ part_acc,
                         float* __restrict__ part_ml, float* __restrict__ scores_out,
                         int* __restrict__ row_done, int B, int S, int d, int chunk_pages, int nstage,
-                        int min_dyn, long long* __restrict__ dbg, unsigned long long* trace) {
+                        int min_dyn, int lengths_final, long long* __restrict__ dbg,
+                        unsigned long long* trace) {
     // optional phase stamps (tools/attn_timing.py): [cta][16]; slots 0-6 clock64 of consumer thread 0,
     // slot 7 = segments << 32 | stages this CTA processed, slots 8-10 %globaltimer at CTA start / end
     // of the last segment / CTA end, slot 11 = segments merged << 32 | rows merged
@@ -183,6 +184,12 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
     const int warp = tid >> 5, lane = tid & 31;
     const int chunk_pos = chunk_pages * kPage;
 
+    // Engine launches (lengths_final): the lengths were written two or more kernels up the dependency
+    // chain, i.e. they are complete and visible before this kernel can start at all, so the first
+    // round of the prefix scan fetches its length here, under the barrier set-up and the dependency
+    // wait.  Stage calls keep every load behind the wait.
+    int len_early = 0;
+    if (FUSED && lengths_final && tid < B) len_early = lengths[tid];
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -211,7 +218,8 @@ decode_attention_kernel(const float* __restrict__ q, float* const* __restrict__ 
         int carry = 0;
         for (int base = 0, round = 0; base < B; base += kAttnThreads, ++round) {
             const int r = base + tid;
-            const int n = (r < B) ? (lengths[r] + G - 1) / G : 0;
+            const int L = (r < B) ? ((lengths_final && round == 0) ? len_early : lengths[r]) : 0;
+            const int n = (L + G - 1) / G;
             int v = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -835,7 +843,7 @@ static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* c
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
     int rc = launch_kernel(ctx, kern, dim3(p.grid), dim3(kAttnThreads), smem, q, page_table, lengths,
                            row_first, item_row, item_chunk, out, part_acc, part_ml, scores_out, row_done,
-                           B, S, d, p.chunk_pages, p.nstage, ctx->attn_min_dyn,
+                           B, S, d, p.chunk_pages, p.nstage, ctx->attn_min_dyn, ctx->attn_lengths_final,
                            reinterpret_cast<long long*>(ctx->tc_dbg), ctx->trace);
     if (rc) return rc;
     if (ctx->attn_ev_stop) MLI_CUDA(cudaEventRecord(ctx->attn_ev_stop, ctx->stream));

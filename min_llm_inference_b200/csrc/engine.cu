@@ -692,8 +692,12 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t g
             ctx->attn_ev_start = ev0;
             ctx->attn_ev_stop = ev1;
         }
+        // lengths[] was last written by the scheduler (round 0) or the previous round's decoder: at least
+        // two kernels up the chain, complete before the attention can start
+        ctx->attn_lengths_final = 1;
         rc = launch_decode_attention_paged(ctx, e->q_out, e->a.page_table, e->a.lengths, e->attn_out,
                                            nullptr, B, S, d);
+        ctx->attn_lengths_final = 0;
         ctx->attn_ev_start = ctx->attn_ev_stop = nullptr;
         if (rc) return rc;
         int n_split = 1;
