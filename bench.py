@@ -279,6 +279,8 @@ def long_context_leg(ctx, torch, hbm_peak):
     return {"workload": "fused decode attention alone, B=1024, d=2048, L~U[64,2048] (BASELINE configs[2] shape)",
             "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "ms_per_launch": ms, "algorithmic_bytes": nbytes,
+            "kernel": "decode_attention_wp_kernel (warp-per-position consumers; the auto rule picks it for launches "
+                      "that can hold >= 1024 positions per SM)",
             "note": "one fused launch per call, 10 calls back to back between one CUDA-event pair"}
 
 
