@@ -52,3 +52,13 @@ def test_product_sources_never_touch_the_oracle():
         if path.is_file() and path.suffix in {".cu", ".cuh", ".h", ".hpp", ".cpp", ".py"}:
             txt = path.read_text()
             assert "oracle/" not in txt and "liboracle" not in txt and "libmli_ref" not in txt, path
+
+
+def test_option_constants_match_the_header():
+    """capi.py's OPT_* values are the header's MLI_OPT_* enum"""
+    enum = dict((k, int(v)) for k, v in re.findall(r"\b(MLI_OPT_\w+)\s*=\s*(\d+)", HEADER))
+    assert len(enum) >= 7
+    for name, value in enum.items():
+        py = "OPT_" + name[len("MLI_OPT_"):]
+        assert getattr(capi, py) == value, f"{py} != {name}"
+        assert getattr(mli, py) == value, f"{py} is not exported by the package"
