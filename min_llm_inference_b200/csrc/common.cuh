@@ -193,14 +193,6 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot)
     }
 }
 
-// the same, recorded by thread 0 of the calling CTA whichever CTA that is
-__device__ __forceinline__ void trace_stamp_cta(unsigned long long* trace, int slot) {
-    if (trace == nullptr || threadIdx.x != 0) return;
-    unsigned long long step = trace[0];
-    if (slot == 0) trace[0] = step + 1; else step -= 1;
-    if (step < trace[1]) trace[8 + 8 * step + slot] = globaltimer_ns();
-}
-
 // Where a kernel releases its dependents.  The heavy kernels (GEMMs, attention, encoder) do it LATE,
 // once their streaming / main loop is over, so that only the dependent's prologue overlaps (with this
 // kernel's tail).  Releasing right after the own wait was measured to be slower: the dependent's CTAs

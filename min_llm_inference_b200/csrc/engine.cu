@@ -22,9 +22,7 @@
 // list (pages are returned in table order), which only changes which page a row gets, never a token.
 #include "common.cuh"
 #include "kernels.h"
-#include "decoder_body.cuh"
 
-#include <cstdlib>
 #include <vector>
 
 namespace mli {
@@ -105,11 +103,7 @@ size_t sched_smem_bytes(int B) {
 // the kernel, and the pages the growth phase hands out come from a shared-memory window of the free
 // ring, so the inherently ordered part of the reference's algorithm (grow in admission order,
 // pre-empt the list tail when the pool is dry) runs without dependent global-memory round trips.
-// ANY_CTA: the body runs in whichever CTA of a larger launch arrived last (decoder_sched_kernel), not in
-// CTA 0 of its own launch: the step trace is stamped by this CTA, and what the decoder CTAs of the same
-// launch wrote (lengths, tokens) is read past this SM's L1, which may hold older copies of those lines.
-template <bool ANY_CTA>
-__device__ __forceinline__ void sched_step_body(const SchedArgs& a) {
+__global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) {
     extern __shared__ __align__(16) unsigned char sched_smem[];
     __shared__ int s_warp[64];
     __shared__ int s_carry[4];
@@ -159,7 +153,7 @@ __device__ __forceinline__ void sched_step_body(const SchedArgs& a) {
     griddep_wait();
     SCHED_PH(2);
     GRIDDEP_TRIGGER_EARLY();
-    if (ANY_CTA) trace_stamp_cta(a.trace, 0); else trace_stamp(a.trace, 0);
+    trace_stamp(a.trace, 0);
     if (sv.done) {
         if (tid == 0) {
             a.v->n_new = 0;
@@ -169,7 +163,7 @@ __device__ __forceinline__ void sched_step_body(const SchedArgs& a) {
         return;
     }
     const bool first = (sv.iter == 0);
-    for (int r = tid; r < B; r += T) s_len[r] = __ldcg(a.lengths + r);
+    for (int r = tid; r < B; r += T) s_len[r] = a.lengths[r];
     __syncthreads();
     SCHED_PH(3);
     int n_used = sv.n_used;
@@ -184,7 +178,7 @@ __device__ __forceinline__ void sched_step_body(const SchedArgs& a) {
             const int id = s_req[r];
             int c = (id >= 0) ? a.req_cnt[id] : 0;
             for (int j = 0; j < R; ++j) {
-                const int t = __ldcg(a.dec + (size_t)r * R + j);
+                const int t = a.dec[(size_t)r * R + j];
                 if (t == MLI_EMPTY_ROW_TOKEN_ID) {
                     empty = true;
                 } else if (id < 0) {
@@ -529,43 +523,6 @@ __device__ __forceinline__ void sched_step_body(const SchedArgs& a) {
 #undef SCHED_PH
 }
 
-__global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) { sched_step_body<false>(a); }
-
-// ---------------------------------------------------------------------------------------------
-// Decoder of step k and scheduler of step k+1 in ONE launch (steps 2..n of a multi-step graph, B <= 256).
-// A dependent-launch hop costs ~2.5 us and a step had six of them; here every decoder CTA (one batch row
-// each) reports with one atomic when its row is done, and the CTA that arrives last -- nobody polls --
-// carries on as the scheduler.  Its block is the decoder's 256 threads, which is the scheduler's own block
-// shape up to 256 rows.
-// ---------------------------------------------------------------------------------------------
-struct DecArgs {
-    const float* score;
-    int n_split;
-    size_t split_stride;
-    const float* pos;
-    const float* emb;
-    int V, d, n_dec, i_dec, kv_bf16;
-    int* arrive;   // CTAs of this launch that are done with their row (re-armed by the last one)
-};
-
-__global__ void __launch_bounds__(256) decoder_sched_kernel(DecArgs da, SchedArgs a) {
-    __shared__ int s_last;
-    griddep_wait();
-    trace_stamp(a.trace, 5);
-    decoder_row<true>(da.score, da.n_split, da.split_stride, nullptr, a.dec, a.lengths, a.page_table, nullptr,
-                      da.pos, da.emb, da.V, a.S, da.d, da.n_dec, da.i_dec, da.kv_bf16, (int)blockIdx.x);
-    __syncthreads();   // the row's stores, then (cumulativity) the fence and the arrival of thread 0
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(da.arrive, 1) == (int)gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (threadIdx.x == 0) *da.arrive = 0;
-    __threadfence();
-    sched_step_body<true>(a);
-}
-
 __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats, int max_req) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = gridDim.x * blockDim.x;
@@ -637,10 +594,7 @@ struct mli_engine {
     cudaEvent_t ev_submit = nullptr, ev_end = nullptr;  // job timing: start of submit .. end of run
     bool submit_timed = false;
     cudaEvent_t ring_ev[4] = {};
-    int launches_per_step = 0;     // kernels in the captured step graph (per graph: x steps per graph)
-    int launches_per_graph[2] = {0, 0};   // [0] one-step graph, [1] multi-step graph
-    bool fuse_sched = false;       // decoder of step k + scheduler of step k+1 in one launch (B <= 256)
-    int* dec_arrive = nullptr;     // arrival counter of that launch
+    int launches_per_step = 0;     // kernels in the captured step graph
     int kv_bf16 = 0;               // page format the engine was created with
     cudaEvent_t prof_ev[32] = {};  // profile mode: one event pair per step of a batch (attention)
     cudaEvent_t prof_gev[32] = {}; // the same for the merged GEMM
@@ -688,7 +642,7 @@ int dev_alloc(mli_engine* e, T** out, size_t n) {
 // the model part of one engine iteration: n_forward_rounds x (encoder -> attention -> decoder)
 // (inference_model.cpp:52-82).  ev0/ev1, when given, bracket the first round's fused attention.
 int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t gev0 = nullptr,
-                  cudaEvent_t gev1 = nullptr, bool sched_next = false) {
+                  cudaEvent_t gev1 = nullptr) {
     mli_ctx* ctx = e->ctx;
     const mli_engine_cfg& c = e->cfg;
     const int B = c.n_batch, S = c.n_sequence, d = c.emb_dim, V = c.n_vocab;
@@ -753,17 +707,10 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t g
         else
             rc = launch_logits_simt(ctx, e->attn_out, e->emb, e->score, B, V, d);
         if (rc) return rc;
-        if (sched_next && round == c.n_forward_rounds - 1) {
-            // last decoder of the step: its last-arriving CTA runs the next step's scheduler in place
-            DecArgs da{e->score, n_split, (size_t)B * V, e->pos, e->emb, V, d, c.n_forward_rounds, round,
-                       ctx->kv_bf16, e->dec_arrive};
-            if ((rc = launch_kernel(ctx, decoder_sched_kernel, dim3(B), dim3(256), sched_smem_bytes(B), da, e->a)))
-                return rc;
-        } else if ((rc = launch_paged_decoder(ctx, e->score, n_split, nullptr, e->a.dec, e->a.lengths,
-                                              e->a.page_table, e->pos, e->emb, B, V, S, d, c.n_forward_rounds,
-                                              round))) {
+        if ((rc = launch_paged_decoder(ctx, e->score, n_split, nullptr, e->a.dec, e->a.lengths,
+                                       e->a.page_table, e->pos, e->emb, B, V, S, d, c.n_forward_rounds,
+                                       round)))
             return rc;
-        }
     }
     return 0;
 }
@@ -772,15 +719,10 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t g
 // previous step), then the model
 // chained = true: the scheduler itself is launched with programmatic dependent launch (it follows
 // the previous step's decoder inside one multi-step graph)
-// sched_next = true: this step's last decoder also schedules the next step (which is then enqueued with
-// chained = true and launches no scheduler of its own)
-int enqueue_step(mli_engine* e, bool chained = false, bool sched_next = false) {
+int enqueue_step(mli_engine* e, bool chained = false) {
     mli_ctx* ctx = e->ctx;
     e->a.trace = ctx->trace;
-    sched_next = sched_next && e->fuse_sched;
-    if (chained && e->fuse_sched) {
-        // scheduled by the previous step's decoder launch
-    } else if (chained && ctx->opt_pdl) {
+    if (chained && ctx->opt_pdl) {
         ctx->use_pdl = true;
         int rc = launch_kernel(ctx, sched_step_kernel, dim3(1), dim3(sched_threads(e->cfg.n_batch)),
                                sched_smem_bytes(e->cfg.n_batch), e->a);
@@ -790,7 +732,7 @@ int enqueue_step(mli_engine* e, bool chained = false, bool sched_next = false) {
         sched_step_kernel<<<1, sched_threads(e->cfg.n_batch), sched_smem_bytes(e->cfg.n_batch), ctx->stream>>>(e->a);
         MLI_LAUNCH_CHECK();
     }
-    return enqueue_model(e, nullptr, nullptr, nullptr, nullptr, sched_next);
+    return enqueue_model(e, nullptr, nullptr);
 }
 
 void drop_graph(mli_engine* e) {
@@ -855,10 +797,6 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     A(dev_alloc(e, &a.dec, (size_t)B * R));
     A(dev_alloc(e, &a.new_idx, B));
     A(dev_alloc(e, &a.act_rows, B));
-    A(dev_alloc(e, &e->dec_arrive, 1));
-    MLI_CUDA(cudaMemset(e->dec_arrive, 0, sizeof(int)));
-    // opt-in (MLI_FUSED_SCHED=1) until it has been validated on hardware
-    e->fuse_sched = B <= 256 && sched_smem_bytes(B) <= 40 * 1024 && getenv("MLI_FUSED_SCHED") != nullptr;
     a.max_gran = B * W;
     A(dev_alloc(e, &a.gran, (size_t)a.max_gran));
     A(dev_alloc(e, &a.counts, 4));
@@ -1072,10 +1010,9 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             MLI_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const long long l0 = mli_kernel_launch_count();
             rc = 0;
-            for (int k = 0; k < per && !rc; ++k) rc = enqueue_step(e, k > 0, k < per - 1);
-            e->launches_per_graph[per == 1 ? 0 : 1] = (int)(mli_kernel_launch_count() - l0);
-            e->launches_per_step = e->launches_per_graph[per == 1 ? 0 : 1] / per;
-            count_launch(-e->launches_per_graph[per == 1 ? 0 : 1]);   // captured, not launched
+            for (int k = 0; k < per && !rc; ++k) rc = enqueue_step(e, k > 0);
+            e->launches_per_step = (int)(mli_kernel_launch_count() - l0) / per;
+            count_launch(-e->launches_per_step * per);   // captured, not launched
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
             if (rc || ce != cudaSuccess) {
                 if (g) cudaGraphDestroy(g);
@@ -1093,7 +1030,7 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
             if (it / per >= kAhead) MLI_CUDA(cudaEventSynchronize(e->ring_ev[slot]));
             if (*reinterpret_cast<volatile int*>(e->done_host)) break;
             MLI_CUDA(cudaGraphLaunch(gexec, ctx->stream));
-            count_launch(e->launches_per_graph[per == 1 ? 0 : 1]);
+            count_launch(e->launches_per_step * per);
             MLI_CUDA(cudaEventRecord(e->ring_ev[slot], ctx->stream));
         }
     }
