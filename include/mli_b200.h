@@ -190,7 +190,9 @@ int mli_dense_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new
  * PagedAttentionsManager (src/paged_item_storage.cpp:14-203, src/item_storage.cpp:97-139).
  * Requests, the page free list, the page table and all admission / retirement / growth /
  * pre-emption decisions live on the device; the host only launches a CUDA graph per step and
- * polls a pinned completion word. */
+ * polls a pinned completion word.
+ * (SURVEY 8b calls these entry points mli_sched_*: create / admit / step / poll / destroy map to
+ * mli_engine_create / _submit + _enqueue / _run / _poll_finished + _results / _destroy.) */
 typedef struct {
     int n_batch, n_sequence, emb_dim, n_vocab;
     int n_blocks;          /* KV pages in the pool */
@@ -201,6 +203,16 @@ typedef struct {
     int max_requests;      /* capacity of the device request table */
     float* page_pool;      /* optional caller-owned slab of n_blocks*16*3*d floats (e.g. the
                               reference's MemoryBlockManager slab); NULL = engine allocates */
+    /* opt-in scheduling policies that the reference does not have (0 = off = the reference's
+     * behaviour); the CPU oracle implements the same two flags so decisions stay comparable */
+    int max_new_tokens;        /* > 0: a request is finished once it has generated this many tokens
+                                  (besides EOF / n_sequence, src/item_storage.cpp:120-124) */
+    int max_prefill_positions; /* > 0: admission throttle: one step admits queued prompts
+                                  only while their positions add up to at most this many (the first
+                                  admission of a step always passes), so an admission burst is spread
+                                  over several steps instead of stalling every decoding row behind one
+                                  huge prefill GEMM (the reference admits everything that fits,
+                                  src/paged_item_storage.cpp:84-113) */
 } mli_engine_cfg;
 
 typedef struct {
@@ -220,6 +232,11 @@ typedef struct {
     double gemm_flops;          /* fp32-equivalent FLOPs of those launches: 6*d*d per active row +
                                    4*d*d per prefill position (the tensor cores execute 3x that in tf32) */
     long long gemm_launches;
+    double gemm_max_flops;      /* profiling only: the largest merged-GEMM launch of the job (the bulk
+                                   prefill, i.e. the tensor-pipe regime) and its device time */
+    float gemm_max_ms;
+    int peak_resident_rows;     /* most rows occupied at once */
+    int min_free_pages;         /* fewest free KV pages seen (pool occupancy = 1 - min_free / n_blocks) */
 } mli_engine_stats;
 
 typedef struct mli_engine mli_engine;
@@ -232,6 +249,15 @@ int mli_engine_destroy(mli_engine* e);
  * DEVICE pointers (is_device = 1, used by bench.py's device-resident leg).  Resets the engine. */
 int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
                       int is_device);
+/* streaming ingestion (replaces ItemStorage::add_new_item being called while the loop of
+ * src/inferencer.cpp:43-85 runs): append requests to a live engine WITHOUT resetting it.  Ids continue
+ * from the last submitted / enqueued request (*first_id, optional, receives the first new id).  The
+ * upload runs on the engine's ingest stream, concurrent with the step graphs; the device scheduler
+ * queues the new requests at its next iteration.  May be called from another host thread while
+ * mli_engine_run executes; requests that arrive after the engine has gone idle are processed by the
+ * next mli_engine_run.  Fails when max_requests would be exceeded. */
+int mli_engine_enqueue(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
+                       int is_device, int* first_id);
 /* run to completion (max_steps <= 0) or for at most max_steps iterations.
  * profile_attention != 0 brackets every fused-attention launch with CUDA events (no graph). */
 int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention);
@@ -239,11 +265,45 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention);
  * tokens[n_req * n_sequence] (prompt + generated) */
 int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, int* finished_tokens,
                        int* n_finished);
+/* asynchronous token return (replaces process_decoder_result's blocking cudaMemcpy +
+ * ItemStorage::pop_finished_items, src/item_storage.cpp:97-139): the requests that finished since the
+ * last poll, in finish order, HOST buffers: ids[max_out], offsets[max_out+1], tokens[tokens_capacity]
+ * (prompt + generated, packed).  Never waits for the engine: the device scheduler publishes its finished
+ * count in mapped pinned memory and the token lists are packed on a side stream while the step graphs
+ * keep running.  Callable from another host thread during mli_engine_run.  *n_out may be 0. */
+int mli_engine_poll_finished(mli_engine* e, int max_out, int* ids, int* offsets, int* tokens,
+                             long long tokens_capacity, int* n_out);
 /* device-to-device copy of the request table (tokens[n_req][n_sequence], counts[n_req]) into
  * caller buffers on the context's stream -- what the multi-GPU token gather (NCCL all-gather,
  * the only collective of the path) sends */
 int mli_engine_copy_tokens(mli_engine* e, int* tokens_dev, int* counts_dev);
 int mli_engine_get_stats(mli_engine* e, mli_engine_stats* stats);
+
+/* ---- multi-GPU: request sharding + the final token gather ------------------------------------- */
+/* The reference is single-GPU (no collective anywhere under /root/reference); its engine
+ * loop (include/inferencer.h:23-32) shards by request with no exchange inside a decode step, so each
+ * GPU runs its own mli_engine on its share of the requests and ONE collective -- an NCCL all-gather of
+ * the per-rank request tables over NVLink / NVSwitch -- returns every finished token list to every
+ * rank.  NCCL is dlopen'ed on first use (libnccl.so.2); single-GPU callers never need it.
+ *   multi-process (one process per GPU, e.g. torchrun): rank 0 calls mli_comm_get_unique_id, ships the
+ *     MLI_COMM_ID_BYTES bytes to the other ranks by any means, every rank calls mli_comm_init_rank;
+ *   single process driving n GPUs: mli_comm_init_all over one context per device; collective calls of
+ *     the n communicators then go between mli_comm_group_start / mli_comm_group_end. */
+#define MLI_COMM_ID_BYTES 128
+typedef struct mli_comm mli_comm;
+int mli_comm_get_unique_id(void* id_out, size_t id_bytes);
+int mli_comm_init_rank(mli_ctx* ctx, int world_size, int rank, const void* unique_id, mli_comm** out);
+int mli_comm_init_all(mli_ctx* const* ctxs, int n, mli_comm** comms_out /* [n] */);
+int mli_comm_group_start(void);
+int mli_comm_group_end(void);
+/* all-gather the engine's request table: all_tokens_dev[world*per_rank][n_sequence] and
+ * all_counts_dev[world*per_rank] (DEVICE buffers of the caller); rank r's requests land at rows
+ * [r*per_rank, (r+1)*per_rank), count 0 = slot unused.  per_rank <= the engine's max_requests.
+ * Stream-ordered on the context's stream after the engine's own stream; no host synchronisation. */
+int mli_comm_gather_tokens(mli_comm* comm, mli_engine* e, int per_rank, int* all_tokens_dev,
+                           int* all_counts_dev);
+int mli_comm_info(mli_comm* comm, int* world_size, int* rank, int* nccl_version);
+int mli_comm_destroy(mli_comm* comm);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ Layout:
   host/      C++ mirror of the reference's classes on top of the C ABI (drop-in headers)
   capi.py    ctypes binding used by tests/ and bench.py (PyTorch only supplies device memory)
 """
-from .capi import (Context, Engine, EngineCfg, EngineStats, MliError, build_library, load_library,
+from .capi import (Context, Engine, Comm, EngineCfg, EngineStats, MliError, build_library, load_library,
                    LIB_PATH, OPT_GEMM_MODE, OPT_ATTN_CHUNK_PAGES, OPT_ATTN_CTAS_PER_SM, OPT_PDL, OPT_KV_FORMAT,
                    OPT_ATTN_KERNEL, OPT_ATTN_MIN_DYN,
                    GEMM_TCGEN05, GEMM_SIMT_EXACT, PAGE_BLOCK_SIZE, EOF_TOKEN_ID,

@@ -38,6 +38,7 @@ class EngineCfg(C.Structure):
         ("n_batch", _I), ("n_sequence", _I), ("emb_dim", _I), ("n_vocab", _I),
         ("n_blocks", _I), ("n_forward_rounds", _I), ("compat_stale_lengths", _I),
         ("max_requests", _I), ("page_pool", _P),
+        ("max_new_tokens", _I), ("max_prefill_positions", _I),
     ]
 
 
@@ -47,6 +48,8 @@ class EngineStats(C.Structure):
         ("n_finished", _I), ("gpu_ms", C.c_float), ("attn_ms", C.c_float),
         ("attn_bytes", C.c_double), ("attn_launches", _LL),
         ("gemm_ms", C.c_float), ("gemm_flops", C.c_double), ("gemm_launches", _LL),
+        ("gemm_max_flops", C.c_double), ("gemm_max_ms", C.c_float),
+        ("peak_resident_rows", _I), ("min_free_pages", _I),
     ]
 
 
@@ -79,11 +82,23 @@ SIGNATURES = {
     "mli_engine_create": (_I, [_P, C.POINTER(EngineCfg)] + [_P] * 5 + [C.POINTER(_P)]),
     "mli_engine_destroy": (_I, [_P]),
     "mli_engine_submit": (_I, [_P, _I, _P, _P, _I]),
+    "mli_engine_enqueue": (_I, [_P, _I, _P, _P, _I, C.POINTER(_I)]),
+    "mli_engine_poll_finished": (_I, [_P, _I, _P, _P, _P, _LL, C.POINTER(_I)]),
     "mli_engine_run": (_I, [_P, _LL, _I]),
     "mli_engine_results": (_I, [_P, _P, _P, _P, C.POINTER(_I)]),
     "mli_engine_copy_tokens": (_I, [_P, _P, _P]),
     "mli_engine_get_stats": (_I, [_P, C.POINTER(EngineStats)]),
+    "mli_comm_get_unique_id": (_I, [_P, C.c_size_t]),
+    "mli_comm_init_rank": (_I, [_P, _I, _I, _P, C.POINTER(_P)]),
+    "mli_comm_init_all": (_I, [C.POINTER(_P), _I, C.POINTER(_P)]),
+    "mli_comm_group_start": (_I, []),
+    "mli_comm_group_end": (_I, []),
+    "mli_comm_gather_tokens": (_I, [_P, _P, _I, _P, _P]),
+    "mli_comm_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "mli_comm_destroy": (_I, [_P]),
 }
+
+COMM_ID_BYTES = 128
 
 
 class MliError(RuntimeError):
@@ -188,6 +203,46 @@ class Context:
         return self.lib.mli_kernel_launch_count()
 
 
+class Comm:
+    """NCCL communicator behind the C ABI (mli_comm_*): the final token gather of a request-sharded job."""
+
+    def __init__(self, ctx: "Context", world: int, rank: int, unique_id: bytes):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.world, self.rank = world, rank
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        h = _P()
+        ctx._check(self.lib.mli_comm_init_rank(ctx.h, world, rank, buf, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        if lib.mli_comm_get_unique_id(buf, COMM_ID_BYTES) != 0:
+            raise MliError(lib.mli_last_error().decode())
+        return buf.raw
+
+    def gather_tokens(self, engine: "Engine", per_rank: int, all_tokens_dev, all_counts_dev):
+        self.ctx._check(self.lib.mli_comm_gather_tokens(self.h, engine.h, per_rank, _ptr(all_tokens_dev),
+                                                        _ptr(all_counts_dev)))
+
+    def nccl_version(self) -> int:
+        v = _I()
+        self.ctx._check(self.lib.mli_comm_info(self.h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mli_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """On-device continuous-batching engine (mli_engine_*)."""
 
@@ -217,6 +272,29 @@ class Engine:
         self.n_req = n_req
         self.ctx._check(self.lib.mli_engine_submit(self.h, n_req, _ptr(prompt_offsets),
                                                    _ptr(prompt_tokens), 1 if is_device else 0))
+
+    def enqueue(self, prompt_offsets, prompt_tokens, is_device=False) -> int:
+        """append requests to the live engine (no reset); returns the id of the first new request"""
+        n_req = len(prompt_offsets) - 1
+        first = _I()
+        self.ctx._check(self.lib.mli_engine_enqueue(self.h, n_req, _ptr(prompt_offsets),
+                                                    _ptr(prompt_tokens), 1 if is_device else 0,
+                                                    C.byref(first)))
+        self.n_req = getattr(self, "n_req", 0) + n_req
+        return first.value
+
+    def poll_finished(self, max_out=None):
+        """requests finished since the last poll (non-blocking): ({id: tokens}, ids in finish order)"""
+        import numpy as np
+        n, S = (max_out or max(self.n_req, 1)), self.cfg.n_sequence
+        ids = np.zeros(n, np.int32)
+        offs = np.zeros(n + 1, np.int32)
+        toks = np.zeros(n * S, np.int32)
+        k = _I()
+        self.ctx._check(self.lib.mli_engine_poll_finished(self.h, n, ids.ctypes.data, offs.ctypes.data,
+                                                          toks.ctypes.data, n * S, C.byref(k)))
+        k = k.value
+        return {int(ids[i]): toks[offs[i]:offs[i + 1]].copy() for i in range(k)}, ids[:k].copy()
 
     def run(self, max_steps=0, profile_attention=False):
         self.ctx._check(self.lib.mli_engine_run(self.h, max_steps, 1 if profile_attention else 0))

@@ -53,6 +53,20 @@ int ws_get_zeroed(mli_ctx* ctx, int slot, size_t bytes, void** out) {
     return 0;
 }
 
+int ensure_dyn_smem_impl(mli_ctx* ctx, const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    for (auto& e : ctx->smem_attr)
+        if (e.first == func) {
+            if (e.second >= bytes) return 0;
+            MLI_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second = bytes;
+            return 0;
+        }
+    MLI_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->smem_attr.push_back({func, bytes});
+    return 0;
+}
+
 static bool use_tc(mli_ctx* ctx) { return ctx->gemm_mode == 0 && ctx->tc_available; }
 
 // tile-list workspace: [int n_tiles | pad to 16 B | TileDesc tiles[max_tiles]]
@@ -157,13 +171,13 @@ int mli_ctx_destroy(mli_ctx* ctx) {
 }
 
 int mli_ctx_set_stream(mli_ctx* ctx, void* cuda_stream) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     return MLI_OK;
 }
 
 int mli_ctx_set_option(mli_ctx* ctx, int option, int value) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     switch (option) {
         case MLI_OPT_GEMM_MODE:
             MLI_REQUIRE(value == 0 || value == 1, "gemm mode must be 0 or 1");
@@ -207,7 +221,8 @@ int mli_ctx_set_option(mli_ctx* ctx, int option, int value) {
 }
 
 int mli_ctx_get_option(mli_ctx* ctx, int option, int* value) {
-    MLI_REQUIRE(ctx && value, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(value, "null argument");
     switch (option) {
         case MLI_OPT_GEMM_MODE: *value = ctx->gemm_mode; return MLI_OK;
         case MLI_OPT_ATTN_CHUNK_PAGES: *value = ctx->attn_chunk_pages; return MLI_OK;
@@ -223,31 +238,31 @@ int mli_ctx_get_option(mli_ctx* ctx, int option, int* value) {
 
 int mli_ctx_register_weights(mli_ctx* ctx, const float* wk, const float* wq, const float* wv,
                              const float* emb_table, int emb_dim, int n_vocab) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     if (!ctx->tc_available) return MLI_OK;  // the SIMT path reads the weights in place
     return tc_register_weights(ctx, wk, wq, wv, emb_table, emb_dim, n_vocab);
 }
 
 int mli_ctx_unregister_weights(mli_ctx* ctx) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     if (ctx->tc_available) tc_unregister_all(ctx);
     return MLI_OK;
 }
 
 int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     ctx->tc_dbg = stamps_dev;
     return MLI_OK;
 }
 
 int mli_debug_set_step_trace(mli_ctx* ctx, void* trace_dev) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     ctx->trace = reinterpret_cast<unsigned long long*>(trace_dev);
     return MLI_OK;
 }
 
 int mli_ctx_synchronize(mli_ctx* ctx) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     MLI_CUDA(cudaStreamSynchronize(ctx->stream));
     return MLI_OK;
 }
@@ -256,7 +271,7 @@ int mli_ctx_synchronize(mli_ctx* ctx) {
 int mli_paged_encoder(mli_ctx* ctx, const float* emb_table, const float* pos_table, const int* inp,
                       float** page_table, const int* lengths, const int* new_item_indices,
                       int n_batch, int n_sequence, int emb_dim, int n_new_items) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     if (n_new_items <= 0) return MLI_OK;  // encoder.cu:138-140
@@ -274,7 +289,7 @@ int mli_paged_encoder(mli_ctx* ctx, const float* emb_table, const float* pos_tab
 int mli_prefill_kv_paged(mli_ctx* ctx, float** page_table, const int* new_batch_idx,
                          const int* lengths, const float* wk, const float* wv, int n_new_items,
                          int n_batch, int n_sequence, int emb_dim) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     if (n_new_items <= 0) return MLI_OK;  // paged_attention.cu:100-102
@@ -292,7 +307,8 @@ int mli_prefill_kv_paged(mli_ctx* ctx, float** page_table, const int* new_batch_
 int mli_qkv_latest_paged(mli_ctx* ctx, float** page_table, const int* lengths, const float* wk,
                          const float* wq, const float* wv, float* q_output, int n_batch,
                          int n_sequence, int emb_dim) {
-    MLI_REQUIRE(ctx && q_output, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(q_output, "null argument");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     return latest_paged(ctx, page_table, lengths, wk, wq, wv, q_output, n_batch, n_sequence, emb_dim);
@@ -301,7 +317,8 @@ int mli_qkv_latest_paged(mli_ctx* ctx, float** page_table, const int* lengths, c
 int mli_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_table,
                                const int* lengths, float* attention_result, float* softmax_out,
                                int n_batch, int n_sequence, int emb_dim) {
-    MLI_REQUIRE(ctx && q && attention_result, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(q && attention_result, "null argument");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     return launch_decode_attention_paged(ctx, q, page_table, lengths, attention_result, softmax_out,
@@ -312,7 +329,8 @@ int mli_paged_attention(mli_ctx* ctx, float** page_table, const int* lengths, co
                         const float* wq, const float* wv, const int* new_batch_idx, float* q_output,
                         float* qkt_output, float* attention_result, int n_new_items, int n_batch,
                         int n_sequence, int emb_dim) {
-    MLI_REQUIRE(ctx && attention_result, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(attention_result, "null argument");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     if (!q_output) {
@@ -334,7 +352,8 @@ int mli_paged_decoder(mli_ctx* ctx, const float* batch_result, const float* emb_
                       float* emb_score, const float* pos_table, float** page_table, int* lengths,
                       int* decoder_result, int n_batch, int n_vocab, int n_sequence, int emb_dim,
                       int n_decoder_results, int i_decoder) {
-    MLI_REQUIRE(ctx && batch_result && decoder_result, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(batch_result && decoder_result, "null argument");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     MLI_REQUIRE(n_vocab > 0 && n_decoder_results > 0 && i_decoder >= 0 &&
@@ -350,7 +369,7 @@ int mli_paged_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new
                       const float* pos_table, float** page_table, const float* wk, const float* wq,
                       const float* wv, float* q_output, float* attention_result, int n_batch,
                       int n_sequence, int emb_dim, int n_vocab, int n_forward_rounds) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
     if (rc) return rc;
     MLI_REQUIRE(n_forward_rounds >= 1 && n_forward_rounds <= kPage, "n_forward_rounds must be 1..16");
@@ -398,7 +417,7 @@ int mli_paged_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new
 int mli_dense_encoder(mli_ctx* ctx, const float* emb_table, const float* pos_table, const int* inp,
                       float* inp_embedding, const int* lengths, const int* new_item_indices,
                       int n_batch, int n_sequence, int emb_dim, int n_new_items) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     MLI_REQUIRE(n_batch > 0 && n_sequence > 0 && emb_dim > 0, "bad dims");
     return launch_dense_encoder(ctx, emb_table, pos_table, inp, inp_embedding, lengths,
                                 new_item_indices, n_sequence, emb_dim, n_new_items);
@@ -408,7 +427,8 @@ int mli_self_attention(mli_ctx* ctx, const float* inp_embedding, const int* leng
                        const float* wq, const float* wv, const int* new_batch_idx, float* kt_cache,
                        float* v_cache, float* q_output, float* qkt_output, float* attention_result,
                        int n_new_items, int n_batch, int n_sequence, int input_dim, int output_dim) {
-    MLI_REQUIRE(ctx && q_output && attention_result, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(q_output && attention_result, "null argument");
     MLI_REQUIRE(n_batch > 0 && n_sequence > 0 && input_dim > 0 && output_dim > 0, "bad dims");
     int rc;
     if (n_new_items > 0) {
@@ -434,7 +454,8 @@ int mli_self_attention(mli_ctx* ctx, const float* inp_embedding, const int* leng
 int mli_dense_decoder(mli_ctx* ctx, const float* batch_result, const float* emb_table,
                       float* emb_score, const float* pos_table, float* inp_embedding, int* lengths,
                       int* decoder_result, int n_batch, int n_vocab, int n_sequence, int emb_dim) {
-    MLI_REQUIRE(ctx && batch_result && decoder_result, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(batch_result && decoder_result, "null argument");
     int rc;
     if (!emb_score) {
         void* p;
@@ -452,7 +473,7 @@ int mli_dense_forward(mli_ctx* ctx, const int* inp, int* lengths, const int* new
                       const float* pos_table, const float* wk, const float* wq, const float* wv,
                       float* inp_embedding, float* kt_cache, float* v_cache, float* q_output,
                       float* attention_result, int n_batch, int n_sequence, int emb_dim, int n_vocab) {
-    MLI_REQUIRE(ctx, "null ctx");
+    MLI_ENTER(ctx, "null ctx");
     int rc;
     void* p;
     if (!q_output) {

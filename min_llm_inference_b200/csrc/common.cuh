@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "mli_b200.h"
 
@@ -36,6 +38,16 @@ void count_launch(int n = 1);
             mli::set_error(std::string("argument error: ") + (msg)); \
             return MLI_ERR_ARG;                                     \
         }                                                           \
+    } while (0)
+
+// every C-ABI entry point that takes a context makes the context's device current first (one process
+// may drive several GPUs, each through its own context)
+#define MLI_ENTER(ctx, msg)                                          \
+    do {                                                            \
+        MLI_REQUIRE((ctx) != nullptr, msg);                         \
+        int _dev = -1;                                              \
+        if (cudaGetDevice(&_dev) != cudaSuccess || _dev != (ctx)->device) \
+            MLI_CUDA(cudaSetDevice((ctx)->device));                 \
     } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -250,10 +262,13 @@ struct mli_ctx {
     int opt_pdl = 1;            // MLI_OPT_PDL
     int kv_bf16 = 0;            // MLI_OPT_KV_FORMAT: 1 = compact pages (K, V in bf16)
     bool use_pdl = false;       // launch_kernel() adds programmatic stream serialization (set by the engine)
-    bool ws_frozen = false;     // set while a CUDA graph that captured ws pointers is alive
+    int ws_frozen = 0;          // number of live CUDA graphs (engines) that captured ws pointers
     // when set, the fused decode-attention main kernel is bracketed by these events (profiling)
     cudaEvent_t attn_ev_start = nullptr, attn_ev_stop = nullptr;
     cudaEvent_t gemm_ev_start = nullptr, gemm_ev_stop = nullptr;   // same for the step's merged GEMM
+    // kernel -> dynamic shared memory this context's DEVICE has been configured for.  The attribute is
+    // per device, so it is tracked per context (one process may drive several GPUs), not per process.
+    std::vector<std::pair<const void*, size_t>> smem_attr;
 };
 
 namespace mli {
@@ -262,6 +277,12 @@ namespace mli {
 int ws_get(mli_ctx* ctx, int slot, size_t bytes, void** out);
 // same, and the buffer is zero-filled whenever it is (re)allocated
 int ws_get_zeroed(mli_ctx* ctx, int slot, size_t bytes, void** out);
+// cudaFuncAttributeMaxDynamicSharedMemorySize >= bytes for `func` on the context's device
+int ensure_dyn_smem_impl(mli_ctx* ctx, const void* func, size_t bytes);
+template <typename F>
+int ensure_dyn_smem(mli_ctx* ctx, F* func, size_t bytes) {
+    return ensure_dyn_smem_impl(ctx, reinterpret_cast<const void*>(func), bytes);
+}
 
 // launch on the context's stream; with ctx->use_pdl the kernel is allowed to start while its
 // predecessor drains (programmatic dependent launch) -- only for kernels that call griddep_wait()

@@ -835,11 +835,7 @@ static int launch_main(const AttnPlan& p, mli_ctx* ctx, const float* q, float* c
                        float* scores_out, int* row_done, int B, int S, int d) {
     auto kern = decode_attention_kernel<NC, G, FUSED, KVB>;
     const size_t smem = p.smem + (FUSED ? sizeof(int) * ((size_t)B + 1) : 0);
-    static size_t configured = 0;  // per instantiation
-    if (configured < smem) {
-        MLI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { int rc0 = ensure_dyn_smem(ctx, kern, smem); if (rc0) return rc0; }
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
     int rc = launch_kernel(ctx, kern, dim3(p.grid), dim3(kAttnThreads), smem, q, page_table, lengths,
                            row_first, item_row, item_chunk, out, part_acc, part_ml, scores_out, row_done,
@@ -1014,12 +1010,7 @@ int launch_decode_attention_dense(mli_ctx* ctx, const float* q, const float* kt_
         set_error("dense attention: n_sequence + emb_dim too large for shared memory");
         return MLI_ERR_UNSUPPORTED;
     }
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        MLI_CUDA(cudaFuncSetAttribute(dense_attention_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { int rc0 = ensure_dyn_smem(ctx, dense_attention_kernel, smem); if (rc0) return rc0; }
     dense_attention_kernel<<<B, 256, smem, ctx->stream>>>(q, kt_cache, v_cache, lengths, out,
                                                           softmax_out, S, d);
     MLI_LAUNCH_CHECK();

@@ -585,11 +585,7 @@ int wp_launch(mli_ctx* ctx, const float* q, float* const* page_table, const int*
               int grid, int min_dyn) {
     auto kern = decode_attention_wp_kernel<NCW, CW, KVB>;
     const size_t smem = wp_smem_bytes(B, d, CW, G, nstage, KVB);
-    static size_t configured = 0;   // per instantiation
-    if (configured < smem) {
-        MLI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { int rc0 = ensure_dyn_smem(ctx, kern, smem); if (rc0) return rc0; }
     if (ctx->attn_ev_start) MLI_CUDA(cudaEventRecord(ctx->attn_ev_start, ctx->stream));
     int rc = launch_kernel(ctx, kern, dim3(grid), dim3(kWpThreads), smem, q, page_table, lengths, out,
                            part_acc, part_ml, row_done, B, S, d, G, nstage, min_dyn,

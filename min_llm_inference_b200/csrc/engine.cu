@@ -23,6 +23,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+#include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace mli {
@@ -31,14 +34,16 @@ struct SchedVars {
     int q_head, q_count, q_cap;
     int f_head, f_count;
     int n_used, n_fin, n_new;
-    int iter, done, error, n_req;
+    int iter, done, error, n_req;   // n_req = requests the scheduler has taken over from the inbox so far
     long long steps, generated, preemptions, admitted;
+    int max_used, min_free;         // peak resident rows / fewest free pages seen (reported, never read back)
 };
 
 struct SchedArgs {
     SchedVars* v;
     int* req_tok;     // [max_req][S]
     int* req_cnt;     // [max_req]
+    int* req_plen;    // [max_req] prompt length at submission (for max_new_tokens)
     int* queue;       // [q_cap] ring of request ids
     int* fin_ids;     // [max_req]
     int* row_req;     // [B]
@@ -56,8 +61,13 @@ struct SchedArgs {
     int* counts;      // [0] = number of active rows, [1] = number of granules
     int max_gran;
     volatile int* done_host;  // mapped pinned
+    volatile int* fin_host;   // mapped pinned: number of finished requests (mli_engine_poll_finished)
+    volatile int* n_avail;    // device: requests whose table rows are complete (written by the ingest stream);
+                              // ids [v->n_req, *n_avail) are waiting to be queued
     unsigned long long* trace;  // optional step timeline
     int B, S, W, R, n_blocks, compat;
+    int max_new;      // > 0: a request is finished once it has generated this many tokens (opt-in)
+    int max_prefill;  // > 0: admission throttle, prompt positions admitted per step (opt-in)
 };
 
 constexpr int kSchedThreads = 1024;
@@ -154,11 +164,15 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     SCHED_PH(2);
     GRIDDEP_TRIGGER_EARLY();
     trace_stamp(a.trace, 0);
-    if (sv.done) {
+    // requests appended by mli_engine_submit / mli_engine_enqueue (the ingest stream publishes the count
+    // after their table rows are complete): ids [sv.n_req, n_avail) are queued in phase 4
+    const int n_avail = *a.n_avail;
+    if (sv.done && n_avail == sv.n_req) {
         if (tid == 0) {
             a.v->n_new = 0;
             a.counts[0] = 0;
             a.counts[1] = 0;
+            *a.done_host = 1;   // (a late arrival may have cleared it; idle again)
         }
         return;
     }
@@ -177,6 +191,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             bool empty = false, finished = false;
             const int id = s_req[r];
             int c = (id >= 0) ? a.req_cnt[id] : 0;
+            // opt-in cap on generated tokens: the request finishes when count - prompt length reaches it
+            const int c_cap = (id >= 0 && a.max_new > 0) ? a.req_plen[id] + a.max_new : 0x7fffffff;
             for (int j = 0; j < R; ++j) {
                 const int t = a.dec[(size_t)r * R + j];
                 if (t == MLI_EMPTY_ROW_TOKEN_ID) {
@@ -188,7 +204,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                     if (c < S) a.req_tok[(size_t)id * S + c] = t;
                     c += 1;
                     ++local_gen;
-                    if (c >= S || t == MLI_EOF_TOKEN_ID) finished = true;
+                    if (c >= S || t == MLI_EOF_TOKEN_ID || c >= c_cap) finished = true;
                 }
                 if (finished || empty) break;
             }
@@ -369,6 +385,11 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     // ================= phase 4: insert_new_items (paged_item_storage.cpp:62-122) =====================
     int k_adm = 0;
     {
+        // newly arrived requests join the tail of the queue in id order (ItemStorage::add_new_item,
+        // item_storage.cpp:190-192)
+        const int n_arrived = n_avail - sv.n_req;
+        for (int k = tid; k < n_arrived; k += T) a.queue[(qh + qc + k) % q_cap] = sv.n_req + k;
+        qc += n_arrived;
         for (int r = tid; r < B; r += T) s_flag[r] = 0;
         __syncthreads();
         for (int i = tid; i < n_used; i += T) s_flag[s_used[i]] = 1;
@@ -387,13 +408,24 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         // nobody gets in and the candidate scans (four block barriers) are skipped
         const int n_cand = (F >= MLI_DEFAULT_INIT_NUM_BLOCKS) ? min(n_free_rows, qc) : 0;
         const int w_used = (fh - sv.f_head + nb) % nb;   // window entries the growth phase consumed
-        // candidate j takes queue item j; admitted iff cumulative page need <= F (a prefix)
-        if (tid == 0) s_carry[0] = 0;
+        // Candidate j (the j-th unoccupied row) takes queue item j.  The reference tests the queue head
+        // against the pages that are free at that moment (:84-88) and stops admitting at the first
+        // head that does not fit (every later row sees the same head and the same pool), so the
+        // admitted candidates are a PREFIX: j is admitted iff every candidate up to j passes
+        //   free pages left after the earlier admissions  >=  need_j = max(4, ceil((len_j + R) / 16)).
+        // A row stores (and the pool gives up) only take_j = min(need_j, W) pages: the reference pops
+        // need_j and cannot represent more than W in the table (the oracle returns the surplus).
+        // Opt-in throttle (max_prefill > 0): a step admits prompts while their positions add up to at
+        // most max_prefill; the first candidate of a step always passes.
+        if (tid == 0) {
+            s_carry[0] = 0;            // pages consumed by the admitted prefix
+            s_carry[1] = 0x7fffffff;   // first candidate that fails
+        }
         __syncthreads();
-        int need_before = 0;
+        int take_before = 0, len_before = 0;
         for (int base = 0; base < n_cand; base += T) {
             const int j = base + tid;
-            int id = -1, len = 0, need = 0;
+            int id = -1, len = 0, need = 0, take = 0;
             if (j < n_cand) {
                 if (base == 0 && qh == sv.q_head && tid < sv.q_count) {
                     id = pq_id;   // nothing was pushed to the front of the queue in this step
@@ -403,31 +435,36 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                     len = a.req_cnt[id];
                 }
                 need = max((len + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
+                take = min(need, W);
             }
-            int totn;
-            const int before = need_before + block_scan_excl(need, &totn, s_warp, scan_phase);
-            const int admit = (j < n_cand && before + need <= F) ? 1 : 0;
-            int tota;
-            (void)block_scan_excl(admit, &tota, s_warp, scan_phase);
-            if (admit) {
+            int tott, totl;
+            const int before = take_before + block_scan_excl(take, &tott, s_warp, scan_phase);
+            const int lbefore = len_before + block_scan_excl(len, &totl, s_warp, scan_phase);
+            const bool ok = before + need <= F &&
+                            (a.max_prefill <= 0 || j == 0 || lbefore + len <= a.max_prefill);
+            if (j < n_cand && !ok) atomicMin(&s_carry[1], j);
+            __syncthreads();
+            const int first_fail = s_carry[1];
+            if (j < n_cand && j < first_fail) {
                 const int row = s_list[j];
-                const int np = min(need, W);
-                for (int t = 0; t < np; ++t) {
+                for (int t = 0; t < take; ++t) {
                     const int wi = w_used + before + t;   // window entry = ring[f_head at entry + wi]
                     a.page_table[(size_t)row * W + t] =
                         (wi < n_fq) ? fq[wi] : a.free_ring[(fh + before + t) % nb];
                 }
-                s_np[row] = np;
+                s_np[row] = take;
                 s_len[row] = len;
                 a.lengths[row] = len;
                 a.len_shadow[row] = len;
                 s_req[row] = id;
                 s_used[n_used + j] = row;
                 a.new_idx[j] = row;
-                atomicMax(&s_carry[0], before + need);   // pages consumed by the admitted prefix
+                atomicMax(&s_carry[0], before + take);
             }
-            k_adm += tota;
-            need_before += totn;
+            k_adm = min(first_fail, min(n_cand, base + T));
+            take_before += tott;
+            len_before += totl;
+            if (first_fail != 0x7fffffff) break;   // uniform: read from shared memory after the barrier
         }
         __syncthreads();
         const int pages_taken = s_carry[0];
@@ -504,12 +541,19 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         v->admitted = sv.admitted + k_adm;
         v->preemptions = sv.preemptions;
         v->iter = sv.iter + 1;
+        v->n_req = n_avail;
+        v->max_used = max(sv.max_used, n_used);
+        v->min_free = min(sv.min_free, F);
         a.counts[0] = n_act;
         a.counts[1] = min(n_gran, a.max_gran);
         if (a.trace != nullptr && a.trace[0] >= 1 && a.trace[0] - 1 < a.trace[1]) {
             a.trace[8 + 8 * (a.trace[0] - 1) + 6] = (unsigned long long)n_act;    // for tools/step_timeline.py
             a.trace[8 + 8 * (a.trace[0] - 1) + 7] = (unsigned long long)n_gran;
         }
+        // finished token lists (written by other threads before the barriers above) are complete in
+        // memory before the host can see the new count
+        __threadfence_system();
+        *a.fin_host = a.v->n_fin;
         // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
         if (n_used + qc == 0) {
             v->done = 1;
@@ -517,6 +561,10 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             __threadfence_system();
         } else {
             v->steps = sv.steps + 1;
+            if (sv.done) {   // requests arrived after the engine had gone idle
+                v->done = 0;
+                *a.done_host = 0;
+            }
         }
     }
     SCHED_PH(9);
@@ -535,7 +583,10 @@ __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats
         for (int j = 0; j < a.R; ++j) a.dec[(size_t)r * a.R + j] = MLI_EMPTY_ROW_TOKEN_ID;
     }
     for (int b = i; b < a.n_blocks; b += n) a.free_ring[b] = pool + (size_t)b * page_floats;
-    for (int q = i; q < max_req; q += n) a.req_cnt[q] = 0;
+    for (int q = i; q < max_req; q += n) {
+        a.req_cnt[q] = 0;
+        a.req_plen[q] = 0;
+    }
     if (i == 0) {
         SchedVars* v = a.v;
         v->q_head = 0; v->q_count = 0; v->q_cap = max_req + 1;
@@ -543,27 +594,76 @@ __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats
         v->n_used = 0; v->n_fin = 0; v->n_new = 0;
         v->iter = 0; v->done = 0; v->error = 0; v->n_req = 0;
         v->steps = 0; v->generated = 0; v->preemptions = 0; v->admitted = 0;
+        v->max_used = 0; v->min_free = a.n_blocks;
         a.counts[0] = 0;
         a.counts[1] = 0;
+        *a.n_avail = 0;
+        *a.fin_host = 0;
     }
 }
 
-// scatter (offsets, tokens) into the request table and queue every request in id order
-__global__ void engine_submit_kernel(SchedArgs a, const int* __restrict__ offs,
-                                     const int* __restrict__ toks, int n_req) {
-    const int q = blockIdx.x;
-    if (q >= n_req) return;
-    const int o = offs[q], n = offs[q + 1] - o;
+// scatter (offsets, tokens) of requests [first, first + n) into the request table.  Lengths that the
+// engine cannot represent are flagged (v->error) and clamped so nothing is written out of bounds:
+//   2 = prompt length outside [1, n_sequence - 1]
+//   3 = a prompt needs more KV pages than the pool has (it could never be admitted)
+__global__ void engine_append_kernel(SchedArgs a, const int* __restrict__ offs,
+                                     const int* __restrict__ toks, int first, int n_req) {
+    const int k = blockIdx.x;
+    if (k >= n_req) return;
+    const int q = first + k;
+    const int o = offs[k];
+    int n = offs[k + 1] - o;
+    int err = 0;
+    if (n < 1 || n + 1 > a.S) {
+        err = 2;
+        n = n < 1 ? 0 : a.S - 1;
+    }
+    const int need = max((n + a.R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
+    if (!err && need > a.n_blocks) err = 3;
     for (int j = threadIdx.x; j < n; j += blockDim.x) a.req_tok[(size_t)q * a.S + j] = toks[o + j];
     if (threadIdx.x == 0) {
-        a.req_cnt[q] = n;
-        a.queue[q] = q;
-        if (q == 0) {
-            a.v->q_head = 0;
-            a.v->q_count = n_req;
-            a.v->n_req = n_req;
-        }
+        a.req_cnt[q] = err ? 0 : n;   // a flagged request is never queued into a row (the job fails)
+        a.req_plen[q] = n;
+        if (err) atomicMax(&a.v->error, err);
     }
+}
+
+// runs after the append kernel on the same stream: the rows are complete, the scheduler may queue them
+__global__ void engine_publish_kernel(SchedArgs a, int n_total) {
+    __threadfence();
+    *a.n_avail = n_total;
+}
+
+// finished requests [first, first + n) in finish order -> ids and exclusive token offsets (one CTA)
+__global__ void engine_fin_offsets_kernel(const int* __restrict__ fin_ids, const int* __restrict__ req_cnt,
+                                          int first, int n, int* __restrict__ out_ids,
+                                          int* __restrict__ out_offs) {
+    __shared__ int s_warp[64];
+    int phase = 0, carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int k = base + threadIdx.x;
+        int id = -1, c = 0;
+        if (k < n) {
+            id = fin_ids[first + k];
+            c = req_cnt[id];
+        }
+        int tot;
+        const int off = carry + block_scan_excl(c, &tot, s_warp, phase);
+        if (k < n) {
+            out_ids[k] = id;
+            out_offs[k] = off;
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0) out_offs[n] = carry;
+}
+
+// token lists of those requests, packed (one CTA per request)
+__global__ void engine_fin_gather_kernel(const int* __restrict__ req_tok, int S, const int* __restrict__ ids,
+                                         const int* __restrict__ offs, int* __restrict__ out_toks) {
+    const int k = blockIdx.x;
+    const int id = ids[k], o = offs[k], c = offs[k + 1] - o;
+    for (int j = threadIdx.x; j < c; j += blockDim.x) out_toks[o + j] = req_tok[(size_t)id * S + j];
 }
 
 }  // namespace mli
@@ -581,15 +681,20 @@ struct mli_engine {
     TileDesc* tiles = nullptr;
     int* n_tiles = nullptr;
     int max_tiles = 0;
-    int* done_host = nullptr;  // mapped pinned
-    int* stage_buf = nullptr;  // device staging for host prompts
+    int* done_host = nullptr;  // mapped pinned: [0] done word, [16] finished count
+    int* stage_buf = nullptr;  // device staging for host prompts (mli_engine_submit / _enqueue)
     size_t stage_ints = 0;
     std::vector<void*> allocs;
     cudaGraphExec_t graph_exec = nullptr;   // one step (bounded runs)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graphn_exec = nullptr;  // kStepsPerGraph steps (runs to completion)
     cudaGraph_t graphn = nullptr;
-    int n_req = 0;
+    bool froze_ws = false;         // this engine holds one count of ctx->ws_frozen
+    bool registered_weights = false;
+    int n_req = 0;                 // requests submitted + enqueued since the last reset
+    int n_polled = 0;              // finished requests already handed out by mli_engine_poll_finished
+    std::mutex mu;                 // guards n_req, stage_buf and the ingest stream (mli_engine_enqueue may
+                                   // be called from another host thread while mli_engine_run executes)
     mli_engine_stats stats{};
     cudaEvent_t ev_submit = nullptr, ev_end = nullptr;  // job timing: start of submit .. end of run
     bool submit_timed = false;
@@ -603,6 +708,13 @@ struct mli_engine {
     // default stream, which cannot be captured into a graph
     cudaStream_t stream = nullptr;
     cudaEvent_t join_ev = nullptr;
+    // streaming side channels: requests come in on `ingest`, finished token lists go out
+    // on `io`, both concurrent with the step graphs on `stream`
+    cudaStream_t ingest = nullptr, io = nullptr;
+    cudaEvent_t reset_ev = nullptr;   // recorded after every reset; the ingest stream waits for it
+    int* res_host = nullptr;          // mapped pinned staging for finished lists: ids | offsets | tokens
+    int* res_dev = nullptr;           // device alias of res_host
+    size_t res_ints = 0;
 };
 
 namespace {
@@ -744,7 +856,98 @@ void drop_graph(mli_engine* e) {
     if (e->graph) cudaGraphDestroy(e->graph);
     e->graph_exec = nullptr;
     e->graph = nullptr;
-    e->ctx->ws_frozen = false;
+    if (e->froze_ws) {   // other engines of the context may still hold captured graphs
+        e->ctx->ws_frozen -= 1;
+        e->froze_ws = false;
+    }
+}
+
+const char* sched_error_text(int code) {
+    switch (code) {
+        case 1: return "engine: a token arrived for a row that is not processing";
+        case 2: return "engine: a prompt length is outside [1, n_sequence - 1]";
+        case 3: return "engine: a prompt needs more KV pages than the pool holds (it could never be admitted)";
+    }
+    return "engine: scheduler error";
+}
+
+// validate host prompts (the device path is validated by engine_append_kernel)
+int check_host_prompts(const mli_engine* e, int n_req, const int* offs) {
+    const int S = e->cfg.n_sequence, R = e->cfg.n_forward_rounds;
+    for (int i = 0; i < n_req; ++i) {
+        const int n = offs[i + 1] - offs[i];
+        MLI_REQUIRE(n >= 1 && n + 1 <= S, "prompt length must be in [1, n_sequence-1]");
+        const int need = std::max((n + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
+        if (need > e->cfg.n_blocks) {
+            set_error("No enough block memories to return: a prompt needs more KV pages than the pool holds");
+            return MLI_ERR_NO_BLOCKS;
+        }
+    }
+    return 0;
+}
+
+// stage (host prompts) and append requests [first, first + n_req) on `st`, then publish the new total.
+// Caller holds e->mu.
+int append_requests(mli_engine* e, int first, int n_req, const int* offs, const int* toks, int is_device,
+                    cudaStream_t st) {
+    if (n_req <= 0) return 0;
+    const int* d_offs = offs;
+    const int* d_toks = toks;
+    if (!is_device) {
+        const int total = offs[n_req] - offs[0];
+        const size_t need = (size_t)n_req + 1 + (size_t)total;
+        if (e->stage_ints < need) {
+            // the previous staging buffer may still be read by an earlier append
+            MLI_CUDA(cudaStreamSynchronize(e->stream));
+            MLI_CUDA(cudaStreamSynchronize(e->ingest));
+            if (e->stage_buf) cudaFree(e->stage_buf);
+            e->stage_buf = nullptr;
+            e->stage_ints = 0;
+            MLI_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->stage_buf), sizeof(int) * need));
+            e->stage_ints = need;
+        }
+        MLI_CUDA(cudaMemcpyAsync(e->stage_buf, offs, sizeof(int) * ((size_t)n_req + 1), cudaMemcpyHostToDevice, st));
+        MLI_CUDA(cudaMemcpyAsync(e->stage_buf + n_req + 1, toks + offs[0], sizeof(int) * (size_t)total,
+                                 cudaMemcpyHostToDevice, st));
+        d_offs = e->stage_buf;
+        d_toks = e->stage_buf + n_req + 1 - offs[0];   // the kernel indexes tokens with the caller's offsets
+    }
+    engine_append_kernel<<<n_req, 128, 0, st>>>(e->a, d_offs, d_toks, first, n_req);
+    MLI_LAUNCH_CHECK();
+    engine_publish_kernel<<<1, 1, 0, st>>>(e->a, first + n_req);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+// finished requests [first, first + n) packed into the mapped pinned staging area on the io stream:
+// res_host = ids[n] | offsets[n + 1] | tokens.  Returns after the io stream has drained (the engine's
+// step graphs keep running on their own stream).
+int gather_finished(mli_engine* e, int first, int n, const int** ids, const int** offs, const int** toks) {
+    const size_t S = (size_t)e->cfg.n_sequence, NR = (size_t)e->cfg.max_requests;
+    const size_t need = 2 * NR + 1 + NR * S;
+    if (e->res_ints < need) {
+        if (e->res_host) cudaFreeHost(e->res_host);
+        e->res_host = nullptr;
+        e->res_ints = 0;
+        MLI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->res_host), sizeof(int) * need, cudaHostAllocMapped));
+        MLI_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->res_dev), e->res_host, 0));
+        e->res_ints = need;
+    }
+    int* d_ids = e->res_dev;
+    int* d_offs = e->res_dev + NR;
+    int* d_toks = e->res_dev + 2 * NR + 1;
+    e->res_host[NR] = 0;
+    if (n > 0) {
+        engine_fin_offsets_kernel<<<1, 1024, 0, e->io>>>(e->a.fin_ids, e->a.req_cnt, first, n, d_ids, d_offs);
+        MLI_LAUNCH_CHECK();
+        engine_fin_gather_kernel<<<n, 256, 0, e->io>>>(e->a.req_tok, (int)S, d_ids, d_offs, d_toks);
+        MLI_LAUNCH_CHECK();
+        MLI_CUDA(cudaStreamSynchronize(e->io));
+    }
+    *ids = e->res_host;
+    *offs = e->res_host + NR;
+    *toks = e->res_host + 2 * NR + 1;
+    return 0;
 }
 
 }  // namespace
@@ -754,22 +957,19 @@ extern "C" {
 int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_table,
                       const float* pos_table, const float* wk, const float* wq, const float* wv,
                       mli_engine** out) {
-    MLI_REQUIRE(ctx && cfg && out, "null argument");
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(cfg && out, "null argument");
     MLI_REQUIRE(cfg->n_batch > 0 && cfg->n_sequence % kPage == 0 && cfg->emb_dim % 4 == 0 &&
                     cfg->n_vocab > 0 && cfg->n_blocks > 0 && cfg->max_requests > 0,
                 "bad engine dims");
     MLI_REQUIRE(cfg->n_forward_rounds >= 1 && cfg->n_forward_rounds <= kPage,
                 "n_forward_rounds must be 1..16");
+    MLI_REQUIRE(cfg->max_new_tokens >= 0 && cfg->max_prefill_positions >= 0, "negative policy value");
     MLI_REQUIRE(sched_smem_bytes(cfg->n_batch) <= 220 * 1024,
                 "n_batch too large for the device scheduler's shared-memory mirrors (max ~10000 rows per GPU)");
     {
-        static size_t configured = 48 * 1024;
-        const size_t need = sched_smem_bytes(cfg->n_batch);
-        if (need > configured) {
-            MLI_CUDA(cudaFuncSetAttribute(sched_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)need));
-            configured = need;
-        }
+        int rc0 = ensure_dyn_smem(ctx, sched_step_kernel, sched_smem_bytes(cfg->n_batch));
+        if (rc0) return rc0;
     }
     mli_engine* e = new mli_engine();
     e->ctx = ctx;
@@ -780,11 +980,14 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     SchedArgs& a = e->a;
     a.B = B; a.S = S; a.W = W; a.R = R; a.n_blocks = cfg->n_blocks;
     a.compat = cfg->compat_stale_lengths;
+    a.max_new = cfg->max_new_tokens;
+    a.max_prefill = cfg->max_prefill_positions;
     int rc = 0;
 #define A(call) if ((rc = (call))) { mli_engine_destroy(e); return rc; }
     A(dev_alloc(e, &a.v, 1));
     A(dev_alloc(e, &a.req_tok, (size_t)NR * S));
     A(dev_alloc(e, &a.req_cnt, NR));
+    A(dev_alloc(e, &a.req_plen, NR));
     A(dev_alloc(e, &a.queue, NR + 1));
     A(dev_alloc(e, &a.fin_ids, NR));
     A(dev_alloc(e, &a.row_req, B));
@@ -800,6 +1003,11 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     a.max_gran = B * W;
     A(dev_alloc(e, &a.gran, (size_t)a.max_gran));
     A(dev_alloc(e, &a.counts, 4));
+    {
+        int* p = nullptr;
+        A(dev_alloc(e, &p, 4));
+        a.n_avail = p;
+    }
     A(dev_alloc(e, &e->q_out, (size_t)B * d));
     A(dev_alloc(e, &e->attn_out, (size_t)B * d));
     A(dev_alloc(e, &e->score, (size_t)kMaxLogitSplit * B * V));   // split-K partial logits
@@ -824,34 +1032,42 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
         e->own_pool = true;
     }
     {
-        cudaError_t ce = cudaHostAlloc(reinterpret_cast<void**>(&e->done_host), 64, cudaHostAllocMapped);
+        cudaError_t ce = cudaHostAlloc(reinterpret_cast<void**>(&e->done_host), 128, cudaHostAllocMapped);
         if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
         int* dptr = nullptr;
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), e->done_host, 0);
         a.done_host = dptr;
-        *e->done_host = 0;
+        a.fin_host = dptr + 16;   // its own 64-byte line
+        e->done_host[0] = 0;
+        e->done_host[16] = 0;
     }
     cudaEventCreate(&e->ev_submit);
     cudaEventCreate(&e->ev_end);
     for (auto& ev : e->ring_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->reset_ev, cudaEventDisableTiming);
     {
         cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->ingest, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->io, cudaStreamNonBlocking);
         if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
     }
 #undef A
     StreamScope scope(e);
     // the engine owns the weight lifetime for as long as it lives: split them once (tcgen05 mode)
-    if (ctx->tc_available &&
-        (rc = tc_register_weights(ctx, wk, wq, wv, emb_table, d, V))) {
-        mli_engine_destroy(e);
-        return rc;
+    if (ctx->tc_available) {
+        if ((rc = tc_register_weights(ctx, wk, wq, wv, emb_table, d, V))) {
+            mli_engine_destroy(e);
+            return rc;
+        }
+        e->registered_weights = true;
     }
     // zero state so a warm-up step is harmless, then run one un-captured step on the empty engine:
     // it sizes every workspace the captured graph will later hold pointers to.
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(a, e->pool, page_floats, NR);
     MLI_LAUNCH_CHECK();
     if ((rc = enqueue_step(e))) { mli_engine_destroy(e); return rc; }
+    cudaEventRecord(e->reset_ev, ctx->stream);
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) { mli_engine_destroy(e); return cuda_fail(ce, __FILE__, __LINE__); }
     *out = e;
@@ -860,16 +1076,25 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
 
 int mli_engine_destroy(mli_engine* e) {
     if (!e) return MLI_OK;
+    MLI_ENTER(e->ctx, "null ctx");
     cudaStreamSynchronize(e->ctx->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->ingest) cudaStreamSynchronize(e->ingest);
+    if (e->io) cudaStreamSynchronize(e->io);
     drop_graph(e);
-    if (e->ctx->tc_available) tc_unregister_weights(e->ctx, e->wk, e->emb);
+    // only what this engine registered (reference-counted: another engine of the context may share
+    // the same weight pointers)
+    if (e->registered_weights) tc_unregister_weights(e->ctx, e->wk, e->emb);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->ingest) cudaStreamDestroy(e->ingest);
+    if (e->io) cudaStreamDestroy(e->io);
     if (e->join_ev) cudaEventDestroy(e->join_ev);
+    if (e->reset_ev) cudaEventDestroy(e->reset_ev);
     for (void* p : e->allocs) cudaFree(p);
     if (e->own_pool && e->pool) cudaFree(e->pool);
     if (e->stage_buf) cudaFree(e->stage_buf);
     if (e->done_host) cudaFreeHost(e->done_host);
+    if (e->res_host) cudaFreeHost(e->res_host);
     if (e->prof_lengths) cudaFreeHost(e->prof_lengths);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
@@ -886,49 +1111,53 @@ int mli_engine_destroy(mli_engine* e) {
 int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
                       int is_device) {
     MLI_REQUIRE(e && prompt_offsets && prompt_tokens, "null argument");
+    MLI_ENTER(e->ctx, "null ctx");
     MLI_REQUIRE(n_req >= 0 && n_req <= e->cfg.max_requests, "too many requests");
     mli_ctx* ctx = e->ctx;
+    int rc;
+    // everything that can fail on the host is checked before the job clock starts
+    if (!is_device && (rc = check_host_prompts(e, n_req, prompt_offsets))) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
     StreamScope scope(e);
     const size_t page_floats = (size_t)kPage * page_pos_floats(e->cfg.emb_dim, e->kv_bf16);
-    const int* d_offs = prompt_offsets;
-    const int* d_toks = prompt_tokens;
+    MLI_CUDA(cudaStreamSynchronize(e->ingest));   // no append of the previous job may still be in flight
     MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
     e->submit_timed = true;
-    if (!is_device) {
-        const int total = prompt_offsets[n_req];
-        for (int i = 0; i < n_req; ++i)
-            MLI_REQUIRE(prompt_offsets[i + 1] - prompt_offsets[i] + 1 <= e->cfg.n_sequence &&
-                            prompt_offsets[i + 1] > prompt_offsets[i],
-                        "prompt length must be in [1, n_sequence-1]");
-        const size_t need = (size_t)n_req + 1 + total;
-        if (e->stage_ints < need) {
-            MLI_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (e->stage_buf) cudaFree(e->stage_buf);
-            e->stage_buf = nullptr;
-            MLI_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->stage_buf), sizeof(int) * need));
-            e->stage_ints = need;
-        }
-        MLI_CUDA(cudaMemcpyAsync(e->stage_buf, prompt_offsets, sizeof(int) * ((size_t)n_req + 1),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-        MLI_CUDA(cudaMemcpyAsync(e->stage_buf + n_req + 1, prompt_tokens, sizeof(int) * (size_t)total,
-                                 cudaMemcpyHostToDevice, ctx->stream));
-        d_offs = e->stage_buf;
-        d_toks = e->stage_buf + n_req + 1;
-    }
-    *e->done_host = 0;
+    e->done_host[0] = 0;
+    e->done_host[16] = 0;
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(e->a, e->pool, page_floats, e->cfg.max_requests);
     MLI_LAUNCH_CHECK();
-    if (n_req > 0) {
-        engine_submit_kernel<<<n_req, 128, 0, ctx->stream>>>(e->a, d_offs, d_toks, n_req);
-        MLI_LAUNCH_CHECK();
-    }
+    if ((rc = append_requests(e, 0, n_req, prompt_offsets, prompt_tokens, is_device, ctx->stream))) return rc;
+    MLI_CUDA(cudaEventRecord(e->reset_ev, ctx->stream));
     e->n_req = n_req;
+    e->n_polled = 0;
     e->stats = mli_engine_stats{};
+    return MLI_OK;
+}
+
+int mli_engine_enqueue(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
+                       int is_device, int* first_id) {
+    MLI_REQUIRE(e && prompt_offsets && prompt_tokens, "null argument");
+    MLI_ENTER(e->ctx, "null ctx");
+    MLI_REQUIRE(n_req >= 0, "negative request count");
+    int rc;
+    if (!is_device && (rc = check_host_prompts(e, n_req, prompt_offsets))) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    MLI_REQUIRE(e->n_req + n_req <= e->cfg.max_requests, "request table full (mli_engine_cfg.max_requests)");
+    // on the ingest stream, concurrent with the step graphs; ordered after the last reset only
+    MLI_CUDA(cudaStreamWaitEvent(e->ingest, e->reset_ev, 0));
+    if ((rc = append_requests(e, e->n_req, n_req, prompt_offsets, prompt_tokens, is_device, e->ingest))) return rc;
+    // the caller may reuse its buffers, and the next append may reuse the staging buffer
+    MLI_CUDA(cudaStreamSynchronize(e->ingest));
+    if (first_id) *first_id = e->n_req;
+    e->n_req += n_req;
+    e->done_host[0] = 0;   // there is work again; the scheduler re-asserts it when everything is finished
     return MLI_OK;
 }
 
 int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     MLI_REQUIRE(e, "null engine");
+    MLI_ENTER(e->ctx, "null ctx");
     mli_ctx* ctx = e->ctx;
     MLI_REQUIRE(ctx->kv_bf16 == e->kv_bf16, "MLI_OPT_KV_FORMAT was changed after the engine was created");
     StreamScope scope(e);
@@ -980,8 +1209,14 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
                     float gms = 0.f;
                     MLI_CUDA(cudaEventElapsedTime(&gms, e->prof_gev[2 * k], e->prof_gev[2 * k + 1]));
                     gemm_ms += gms;
-                    gemm_flops += (6.0 * slot[B] + 4.0 * kPage * slot[B + 1]) * (double)d * d;
+                    const double fl = (6.0 * slot[B] + 4.0 * kPage * slot[B + 1]) * (double)d * d;
+                    gemm_flops += fl;
                     ++gemm_launches;
+                    // the largest launch of the job (bulk prefill: the tensor-pipe regime)
+                    if (fl > e->stats.gemm_max_flops) {
+                        e->stats.gemm_max_flops = fl;
+                        e->stats.gemm_max_ms = gms;
+                    }
                 }
                 float ms = 0.f;
                 MLI_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]));
@@ -1021,7 +1256,10 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
                 return rc ? rc : cuda_fail(ce, __FILE__, __LINE__);
             }
             MLI_CUDA(cudaGraphInstantiate(&gexec, g, 0));
-            ctx->ws_frozen = true;
+            if (!e->froze_ws) {
+                ctx->ws_frozen += 1;
+                e->froze_ws = true;
+            }
         }
         const int kAhead = (per == 1) ? 4 : MLI_GRAPHS_AHEAD;   // graphs in flight before the host looks at `done`
         for (;; it += per) {
@@ -1052,9 +1290,11 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     e->stats.gemm_ms = gemm_ms;
     e->stats.gemm_flops = gemm_flops;
     e->stats.gemm_launches = gemm_launches;
+    e->stats.peak_resident_rows = hv.max_used;
+    e->stats.min_free_pages = hv.min_free;
     if (hv.error) {
-        set_error("engine: a token arrived for a row that is not processing");
-        return MLI_ERR_STATE;
+        set_error(sched_error_text(hv.error));
+        return hv.error == 3 ? MLI_ERR_NO_BLOCKS : (hv.error == 2 ? MLI_ERR_ARG : MLI_ERR_STATE);
     }
     return MLI_OK;
 }
@@ -1063,32 +1303,49 @@ int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, 
                        int* n_finished) {
     MLI_REQUIRE(e && finished_ids && finished_offsets && finished_tokens && n_finished,
                 "null argument");
+    MLI_ENTER(e->ctx, "null ctx");
     mli_ctx* ctx = e->ctx;
-    const int S = e->cfg.n_sequence, NR = e->n_req;
     MLI_CUDA(cudaStreamSynchronize(e->stream));
     MLI_CUDA(cudaStreamSynchronize(ctx->stream));
-    SchedVars hv;
-    MLI_CUDA(cudaMemcpy(&hv, e->a.v, sizeof(hv), cudaMemcpyDeviceToHost));
-    std::vector<int> cnt(NR > 0 ? NR : 1), toks((size_t)(NR > 0 ? NR : 1) * S);
-    MLI_CUDA(cudaMemcpy(finished_ids, e->a.fin_ids, sizeof(int) * (size_t)hv.n_fin,
-                        cudaMemcpyDeviceToHost));
-    MLI_CUDA(cudaMemcpy(cnt.data(), e->a.req_cnt, sizeof(int) * (size_t)NR, cudaMemcpyDeviceToHost));
-    MLI_CUDA(cudaMemcpy(toks.data(), e->a.req_tok, sizeof(int) * (size_t)NR * S,
-                        cudaMemcpyDeviceToHost));
-    int o = 0;
-    for (int i = 0; i < hv.n_fin; ++i) {
-        const int id = finished_ids[i];
-        finished_offsets[i] = o;
-        for (int j = 0; j < cnt[id]; ++j) finished_tokens[o + j] = toks[(size_t)id * S + j];
-        o += cnt[id];
-    }
-    finished_offsets[hv.n_fin] = o;
-    *n_finished = hv.n_fin;
+    std::lock_guard<std::mutex> lk(e->mu);
+    // everything is final: the count the scheduler last published is exact
+    const int n_fin = *reinterpret_cast<volatile int*>(e->done_host + 16);
+    const int *ids, *offs, *toks;
+    int rc = gather_finished(e, 0, n_fin, &ids, &offs, &toks);
+    if (rc) return rc;
+    // one packed device-to-host transfer happened (the gather kernels wrote pinned memory); hand it out
+    memcpy(finished_ids, ids, sizeof(int) * (size_t)n_fin);
+    memcpy(finished_offsets, offs, sizeof(int) * ((size_t)n_fin + 1));
+    memcpy(finished_tokens, toks, sizeof(int) * (size_t)offs[n_fin]);
+    *n_finished = n_fin;
+    return MLI_OK;
+}
+
+int mli_engine_poll_finished(mli_engine* e, int max_out, int* ids_out, int* offsets_out, int* tokens_out,
+                             long long tokens_capacity, int* n_out) {
+    MLI_REQUIRE(e && ids_out && offsets_out && tokens_out && n_out, "null argument");
+    MLI_ENTER(e->ctx, "null ctx");
+    std::lock_guard<std::mutex> lk(e->mu);
+    const int n_fin = *reinterpret_cast<volatile int*>(e->done_host + 16);
+    int n = std::min(std::max(n_fin - e->n_polled, 0), std::max(max_out, 0));
+    *n_out = 0;
+    offsets_out[0] = 0;
+    if (n == 0) return MLI_OK;
+    const int *ids, *offs, *toks;
+    int rc = gather_finished(e, e->n_polled, n, &ids, &offs, &toks);
+    if (rc) return rc;
+    while (n > 0 && (long long)offs[n] > tokens_capacity) --n;   // hand out only what fits
+    memcpy(ids_out, ids, sizeof(int) * (size_t)n);
+    memcpy(offsets_out, offs, sizeof(int) * ((size_t)n + 1));
+    memcpy(tokens_out, toks, sizeof(int) * (size_t)offs[n]);
+    e->n_polled += n;
+    *n_out = n;
     return MLI_OK;
 }
 
 int mli_engine_copy_tokens(mli_engine* e, int* tokens_dev, int* counts_dev) {
     MLI_REQUIRE(e && tokens_dev && counts_dev, "null argument");
+    MLI_ENTER(e->ctx, "null ctx");
     mli_ctx* ctx = e->ctx;
     MLI_CUDA(cudaStreamSynchronize(e->stream));
     MLI_CUDA(cudaMemcpyAsync(tokens_dev, e->a.req_tok,
@@ -1106,3 +1363,18 @@ int mli_engine_get_stats(mli_engine* e, mli_engine_stats* stats) {
 }
 
 }  // extern "C"
+
+// internal to the library (comm.cu): what the token gather sends
+namespace mli {
+int engine_token_table(mli_engine* e, const int** tokens_dev, const int** counts_dev, int* capacity,
+                       int* n_sequence, cudaStream_t* engine_stream, mli_ctx** ctx) {
+    MLI_REQUIRE(e, "null engine");
+    if (tokens_dev) *tokens_dev = e->a.req_tok;
+    if (counts_dev) *counts_dev = e->a.req_cnt;
+    if (capacity) *capacity = e->cfg.max_requests;
+    if (n_sequence) *n_sequence = e->cfg.n_sequence;
+    if (engine_stream) *engine_stream = e->stream;
+    if (ctx) *ctx = e->ctx;
+    return MLI_OK;
+}
+}  // namespace mli

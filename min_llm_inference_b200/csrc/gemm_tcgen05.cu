@@ -680,6 +680,7 @@ struct OperandEntry {
     const float *k0, *k1, *k2;  // identifying pointers
     int rows, K;
     bool registered;
+    int refs;       // registrations alive (engines / layers sharing one weight set on this context)
     float *hi, *lo;
     CUtensorMap map_hi, map_lo;
 };
@@ -824,12 +825,7 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     args.trace_slot = (args.mode == TC_LOGITS) ? 4 : 2;
     const size_t smem = tc_smem_bytes(nst, bn);
 
-    static bool configured = false;
-    if (!configured) {
-        MLI_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc_smem_bytes(2, kMaxBN)));
-        configured = true;
-    }
+    { int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_kernel, tc_smem_bytes(2, kMaxBN)); if (rc0) return rc0; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);
     cfg.blockDim = dim3(kTcThreadsV2);
@@ -867,12 +863,15 @@ int tc_register_weights(mli_ctx* ctx, const float* wk, const float* wq, const fl
     if (wk && wq && wv && shapes_ok(d, d)) {
         if ((rc = get_operand(ctx, wk, wq, wv, 3 * d, d, &e))) return rc;
         e->registered = true;
+        e->refs += 1;
         if ((rc = get_operand(ctx, wk, wv, nullptr, 2 * d, d, &e))) return rc;
         e->registered = true;
+        e->refs += 1;
     }
     if (emb && shapes_ok(d, V)) {
         if ((rc = get_operand(ctx, emb, nullptr, nullptr, V, d, &e))) return rc;
         e->registered = true;
+        e->refs += 1;
     }
     return 0;
 }
@@ -883,7 +882,9 @@ void tc_unregister_weights(mli_ctx* ctx, const float* wk, const float* emb) {
     cudaStreamSynchronize(ctx->stream);
     for (size_t i = 0; i < st->ops.size();) {
         OperandEntry& e = st->ops[i];
-        if (e.registered && ((wk && e.k0 == wk) || (emb && e.k0 == emb))) {
+        if (e.registered && ((wk && e.k0 == wk) || (emb && e.k0 == emb)) && --e.refs > 0) {
+            ++i;   // another engine / layer still uses this copy (and may hold it in a captured graph)
+        } else if (e.registered && ((wk && e.k0 == wk) || (emb && e.k0 == emb))) {
             cudaFree(e.hi);
             cudaFree(e.lo);
             st->ops.erase(st->ops.begin() + i);

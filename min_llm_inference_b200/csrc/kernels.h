@@ -101,4 +101,9 @@ int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, 
                          float* inp_embedding, const float* pos, const float* emb, int B, int V, int S,
                          int d);
 
+
+// ---- engine internals used by the token gather (comm.cu) ----------------------------------------
+int engine_token_table(mli_engine* e, const int** tokens_dev, const int** counts_dev, int* capacity,
+                       int* n_sequence, cudaStream_t* engine_stream, mli_ctx** ctx);
+
 }  // namespace mli

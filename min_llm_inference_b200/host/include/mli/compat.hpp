@@ -85,6 +85,11 @@ mli_ctx* host_context();
 void check(int status);
 void set_fix_stale_lengths(bool on);
 bool fix_stale_lengths();
+// request-sharded multi-GPU run of the paged engines inside one process (MLI_NUM_GPUS=n or
+// set_num_gpus(n)): GPU g takes the g-th contiguous block of queued requests; the finished token
+// lists come back through mli_comm_gather_tokens (NCCL all-gather)
+void set_num_gpus(int n);
+int num_gpus();
 }  // namespace mli
 
 // ---- Tensor (include/tensor.hpp) -----------------------------------------------------------------------

@@ -465,6 +465,8 @@ typedef struct {
     int n_req, S;
     int* tok;  /* [n_req][S] prompt + generated */
     int* cnt;  /* [n_req] */
+    int* plen; /* [n_req] prompt length at submission */
+    int max_new; /* opt-in policy (not in the reference): > 0 = finish after this many generated tokens */
     /* Storage new_items_ (src/item_storage.cpp:12-95): deque of request ids */
     int* q;
     int qcap, qhead, qcount;
@@ -478,6 +480,8 @@ static void rs_init(req_store* rs, int n_req, int S, const int* off, const int* 
     rs->S = S;
     rs->tok = (int*)calloc((size_t)n_req * S, sizeof(int));
     rs->cnt = (int*)calloc((size_t)n_req, sizeof(int));
+    rs->plen = (int*)calloc((size_t)n_req, sizeof(int));
+    rs->max_new = 0;
     rs->qcap = n_req + 1;
     rs->q = (int*)malloc(sizeof(int) * (size_t)rs->qcap);
     rs->qhead = 0;
@@ -488,11 +492,12 @@ static void rs_init(req_store* rs, int n_req, int S, const int* off, const int* 
         int n = off[i + 1] - off[i];
         memcpy(rs->tok + (size_t)i * S, toks + off[i], sizeof(int) * (size_t)n);
         rs->cnt[i] = n;
+        rs->plen[i] = n;
         rs->q[(rs->qhead + rs->qcount++) % rs->qcap] = i; /* add_new_item: push_back */
     }
 }
 static void rs_free(req_store* rs) {
-    free(rs->tok); free(rs->cnt); free(rs->q); free(rs->fin);
+    free(rs->tok); free(rs->cnt); free(rs->plen); free(rs->q); free(rs->fin);
 }
 static int rs_pop_front(req_store* rs) {
     int id = rs->q[rs->qhead];
@@ -539,6 +544,7 @@ static int process_decoder_result(const int* dec, int B, int R, int S, req_store
                 rs->cnt[id]++;
                 (*gen)++;
                 if (rs->cnt[id] >= S || t == ORC_EOF_TOKEN) finished = 1;
+                if (rs->max_new > 0 && rs->cnt[id] - rs->plen[id] >= rs->max_new) finished = 1; /* opt-in */
             }
             if (finished || empty) break;
         }
@@ -649,8 +655,10 @@ static void allocate_or_free(paged_state* ps, req_store* rs, const int* finished
 
 /* src/paged_item_storage.cpp:62-122 (paged insert_new_items).  Returns n_new; the row indices
  * are in ps->idx_dev[0..n_new). */
-static int paged_insert_new_items(paged_state* ps, req_store* rs, int fix_stale_lengths) {
+static int paged_insert_new_items(paged_state* ps, req_store* rs, int fix_stale_lengths,
+                                  int max_prefill) {
     int B = ps->B, S = ps->S, W = ps->W, R = ps->R;
+    int admitted_positions = 0; /* opt-in admission throttle (not in the reference; 0 = off) */
     char* occ = (char*)calloc((size_t)B, 1);
     for (int p = 0; p < ps->n_used; ++p) occ[ps->used_rows[p]] = 1;
     if (fix_stale_lengths) memcpy(ps->len_host, ps->len_dev, sizeof(int) * (size_t)B);
@@ -658,9 +666,11 @@ static int paged_insert_new_items(paged_state* ps, req_store* rs, int fix_stale_
     for (int i = 0; i < B; ++i) {
         if (occ[i]) continue;
         if (ps->fcount >= ORC_INIT_BLOCKS && rs->qcount > 0 &&
-            ps->fcount >= ceil_div_i(rs_head_len(rs) + R, ORC_PAGE_BLOCK)) {
+            ps->fcount >= ceil_div_i(rs_head_len(rs) + R, ORC_PAGE_BLOCK) &&
+            (max_prefill <= 0 || n_new == 0 || admitted_positions + rs_head_len(rs) <= max_prefill)) {
             int id = rs_pop_front(rs);
             int len = rs->cnt[id];
+            admitted_positions += len;
             ps->len_host[i] = len;
             memcpy(ps->inp_host + (size_t)i * S, rs->tok + (size_t)id * S, sizeof(int) * (size_t)len);
             ps->idx_host[n_new++] = i;
@@ -737,7 +747,8 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
     long long steps = 0, gen = 0, pre = 0;
     int rc = 0, phantom = 0;
 
-    int n_new = paged_insert_new_items(&ps, &rs, cfg->fix_stale_lengths);
+    rs.max_new = cfg->max_new_tokens;
+    int n_new = paged_insert_new_items(&ps, &rs, cfg->fix_stale_lengths, cfg->max_prefill_positions);
     for (;;) {
         int processing = 0;
         for (int i = 0; i < B; ++i) processing += (ps.row_req[i] >= 0);
@@ -749,7 +760,7 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
                                         &phantom);
         if (phantom) { rc = -3; break; }
         allocate_or_free(&ps, &rs, finished_indices, nf, &pre);
-        n_new = paged_insert_new_items(&ps, &rs, cfg->fix_stale_lengths);
+        n_new = paged_insert_new_items(&ps, &rs, cfg->fix_stale_lengths, cfg->max_prefill_positions);
         ++steps;
     }
     emit_finished(&rs, finished_ids, finished_offsets, finished_tokens);
@@ -775,6 +786,7 @@ int orc_dense_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
     int B = cfg->n_batch, S = cfg->n_sequence, d = cfg->emb_dim, V = cfg->n_vocab;
     req_store rs;
     rs_init(&rs, n_req, S, prompt_offsets, prompt_tokens);
+    rs.max_new = cfg->max_new_tokens;
     int* inp = (int*)calloc((size_t)B * S, sizeof(int));
     int* len = (int*)calloc((size_t)B, sizeof(int));
     int* idx = (int*)calloc((size_t)B, sizeof(int));

@@ -119,6 +119,11 @@ typedef struct {
     int fix_stale_lengths; /* 0 = reproduce reference quirk Q1 (paged_item_storage.cpp:62-118),
                               1 = refresh host lengths from the device before every insert */
     int max_steps;         /* safety cap on loop iterations; <=0 = unlimited */
+    /* opt-in scheduling policies of the product's engine that the reference does not have (0 = off =
+     * the reference's behaviour); restated here so scheduler decisions stay comparable */
+    int max_new_tokens;        /* > 0: a request is finished once it has generated this many tokens */
+    int max_prefill_positions; /* > 0: one insert_new_items call admits prompts only while their
+                                  positions add up to at most this many (the first always passes) */
 } orc_engine_cfg;
 
 typedef struct {
