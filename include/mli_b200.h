@@ -129,6 +129,24 @@ int mli_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_
                                const int* lengths, float* attention_result, float* softmax_out,
                                int n_batch, int n_sequence, int emb_dim);
 
+/* The reference's three unfused stages, one launch each, for callers (and the reference's kernel tests,
+ * tests/paged_attention_kernels_test.cpp:115-169) written against them.  Not used by the product path.
+ * They keep the reference's summation order, so scores and P.V are bit-identical to its kernels.
+ * replaces launch_qkt_paged_attention (paged_attention.h:37-39; paged_attention.cu:208-280):
+ * qkt_output[r][j] = (q[r] . K[r][j]) / sqrtf(d) for j < lengths[r]; other entries untouched */
+int mli_qkt_paged(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
+                  float* qkt_output, int n_batch, int n_sequence, int emb_dim);
+/* replaces launch_softmax_in_place_with_lengths (self_attention_inference_optimized.h:21-22;
+ * self_attention_inference_optimized.cu:191-242, :360-368): softmax over the first lengths[r]
+ * entries of every row, zeros up to n_sequence */
+int mli_softmax_in_place_with_lengths(mli_ctx* ctx, float* qkt_output, const int* lengths, int n_batch,
+                                      int n_sequence);
+/* replaces launch_softmax_v_paged_attention (paged_attention.h:41-43; paged_attention.cu:287-345):
+ * attention_result[r][c] = sum_{j < lengths[r]} softmax_result[r][j] * V[r][j][c] */
+int mli_softmax_v_paged(mli_ctx* ctx, const float* softmax_result, float* const* page_table,
+                        float* attention_result, const int* lengths, int n_batch, int n_sequence,
+                        int emb_dim);
+
 /* replaces paged_attention / paged_attention_with_cublas (paged_attention.h:17-26, :46-55;
  * paged_attention.cu:358-377): prefill(new rows) -> latest QKV -> fused decode attention.
  * qkt_output may be NULL (the fused kernel needs no [B,S] scratch). */

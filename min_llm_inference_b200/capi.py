@@ -72,6 +72,9 @@ SIGNATURES = {
     "mli_prefill_kv_paged": (_I, [_P] * 6 + [_I] * 4),
     "mli_qkv_latest_paged": (_I, [_P] * 7 + [_I] * 3),
     "mli_decode_attention_paged": (_I, [_P] * 6 + [_I] * 3),
+    "mli_qkt_paged": (_I, [_P] * 5 + [_I] * 3),
+    "mli_softmax_in_place_with_lengths": (_I, [_P] * 3 + [_I] * 2),
+    "mli_softmax_v_paged": (_I, [_P] * 5 + [_I] * 3),
     "mli_paged_attention": (_I, [_P] * 10 + [_I] * 4),
     "mli_paged_decoder": (_I, [_P] * 8 + [_I] * 6),
     "mli_paged_forward": (_I, [_P] * 5 + [_I] + [_P] * 8 + [_I] * 5),

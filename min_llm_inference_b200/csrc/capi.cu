@@ -325,6 +325,35 @@ int mli_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_
                                          n_batch, n_sequence, emb_dim);
 }
 
+int mli_qkt_paged(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
+                  float* qkt_output, int n_batch, int n_sequence, int emb_dim) {
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(q && page_table && lengths && qkt_output, "null argument");
+    int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
+    if (rc) return rc;
+    MLI_REQUIRE(!ctx->kv_bf16, "the unfused stages read the reference's fp32 page format only");
+    return launch_qkt_unfused(ctx, q, page_table, lengths, qkt_output, n_batch, n_sequence, emb_dim);
+}
+
+int mli_softmax_in_place_with_lengths(mli_ctx* ctx, float* qkt_output, const int* lengths, int n_batch,
+                                      int n_sequence) {
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(qkt_output && lengths && n_batch > 0 && n_sequence > 0, "bad argument");
+    return launch_softmax_lengths_unfused(ctx, qkt_output, lengths, n_batch, n_sequence);
+}
+
+int mli_softmax_v_paged(mli_ctx* ctx, const float* softmax_result, float* const* page_table,
+                        float* attention_result, const int* lengths, int n_batch, int n_sequence,
+                        int emb_dim) {
+    MLI_ENTER(ctx, "null ctx");
+    MLI_REQUIRE(softmax_result && page_table && attention_result && lengths, "null argument");
+    int rc = check_paged_dims(n_batch, n_sequence, emb_dim);
+    if (rc) return rc;
+    MLI_REQUIRE(!ctx->kv_bf16, "the unfused stages read the reference's fp32 page format only");
+    return launch_softmax_v_unfused(ctx, softmax_result, page_table, attention_result, lengths, n_batch,
+                                    n_sequence, emb_dim);
+}
+
 int mli_paged_attention(mli_ctx* ctx, float** page_table, const int* lengths, const float* wk,
                         const float* wq, const float* wv, const int* new_batch_idx, float* q_output,
                         float* qkt_output, float* attention_result, int n_new_items, int n_batch,

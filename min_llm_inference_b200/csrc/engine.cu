@@ -693,6 +693,8 @@ struct mli_engine {
     bool registered_weights = false;
     int n_req = 0;                 // requests submitted + enqueued since the last reset
     int n_polled = 0;              // finished requests already handed out by mli_engine_poll_finished
+    bool pending_wake = false;     // requests were enqueued since the last run started: the done word may be
+                                   // stale (the device can set it before it has seen them)
     std::mutex mu;                 // guards n_req, stage_buf and the ingest stream (mli_engine_enqueue may
                                    // be called from another host thread while mli_engine_run executes)
     mli_engine_stats stats{};
@@ -1131,6 +1133,7 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
     MLI_CUDA(cudaEventRecord(e->reset_ev, ctx->stream));
     e->n_req = n_req;
     e->n_polled = 0;
+    e->pending_wake = false;
     e->stats = mli_engine_stats{};
     return MLI_OK;
 }
@@ -1151,7 +1154,7 @@ int mli_engine_enqueue(mli_engine* e, int n_req, const int* prompt_offsets, cons
     MLI_CUDA(cudaStreamSynchronize(e->ingest));
     if (first_id) *first_id = e->n_req;
     e->n_req += n_req;
-    e->done_host[0] = 0;   // there is work again; the scheduler re-asserts it when everything is finished
+    e->pending_wake = true;   // the next mli_engine_run looks at the device state, not at a stale done word
     return MLI_OK;
 }
 
@@ -1167,6 +1170,15 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     double attn_bytes = 0.0, gemm_flops = 0.0;
     long long attn_launches = 0, gemm_launches = 0;
     MLI_CUDA(cudaEventRecord(e->ring_ev[0], ctx->stream));  // make ring events valid
+    {
+        // requests enqueued since the last run: launch at least one step, whose scheduler either takes
+        // them over or finds nothing new and re-asserts the done word itself
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (e->pending_wake) {
+            e->done_host[0] = 0;
+            e->pending_wake = false;
+        }
+    }
     // device time of the job: from the start of the submit that fed this run (else from here)
     if (!e->submit_timed) MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
     e->submit_timed = false;

@@ -88,6 +88,12 @@ bool attention_wp_usable(mli_ctx* ctx, int B, int d);
 int launch_decode_attention_wp(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
                                float* out, float* part_acc, float* part_ml, int* row_done, int B, int S,
                                int d, int min_dyn);
+// the reference's three unfused stages as stand-alone launches (API completeness; not on the product path)
+int launch_qkt_unfused(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths, float* qkt,
+                       int B, int S, int d);
+int launch_softmax_lengths_unfused(mli_ctx* ctx, float* qkt, const int* lengths, int B, int S);
+int launch_softmax_v_unfused(mli_ctx* ctx, const float* p, float* const* page_table, float* out,
+                             const int* lengths, int B, int S, int d);
 double attention_algorithmic_bytes(const int* lengths_host, int B, int d, int kv_bf16 = 0);
 
 // ---- decoder (src/kernels/decoder.cu:25-91, :128-205) -------------------------------------------

@@ -248,4 +248,124 @@ int launch_dense_decoder(mli_ctx* ctx, const float* score, int* decoder_result, 
                          static_cast<unsigned long long*>(nullptr), 0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The reference's three UNFUSED attention stages, kept as stand-alone launches so that code (and the
+// reference's own kernel tests, tests/paged_attention_kernels_test.cpp:115-169) written against
+//   launch_qkt_paged_attention               src/kernels/paged_attention.cu:208-280
+//   launch_softmax_in_place_with_lengths     src/kernels/self_attention_inference_optimized.cu:191-242
+//   launch_softmax_v_paged_attention         src/kernels/paged_attention.cu:287-345
+// still has something to call.  The product path never uses them (it runs the fused kernel); they keep
+// the reference's summation ORDER -- one k-ascending FMA chain per score, one j-ascending chain per
+// output column -- so scores and P.V are bit-identical to the reference's kernels.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQktKc = 128;   // k columns staged per pass
+
+// grid (W, B), 128 threads: the CTA stages a [16 positions][128 columns] slab of K with coalesced
+// loads; thread p < 16 owns position p of the page and runs the reference's sequential chain
+__global__ void __launch_bounds__(128)
+qkt_unfused_kernel(const float* __restrict__ q, float* const* __restrict__ page_table,
+                   const int* __restrict__ lengths, float* __restrict__ qkt, int S, int d) {
+    __shared__ float ks[kPage][kQktKc + 1];
+    __shared__ float qs[kQktKc];
+    const int r = blockIdx.y, pg = blockIdx.x, tid = threadIdx.x;
+    const int L = lengths[r];
+    const int j0 = pg * kPage;
+    if (j0 >= L) return;
+    const int np = min(kPage, L - j0);
+    const float* page = page_table[(size_t)r * (S / kPage) + pg];
+    float acc = 0.f;
+    for (int c0 = 0; c0 < d; c0 += kQktKc) {
+        const int nc = min(kQktKc, d - c0);
+        for (int i = tid; i < nc; i += 128) qs[i] = q[(size_t)r * d + c0 + i];
+        for (int i = tid; i < np * kQktKc; i += 128) {
+            const int p = i / kQktKc, c = i % kQktKc;
+            if (c < nc) ks[p][c] = page[(size_t)p * 3 * d + d + c0 + c];
+        }
+        __syncthreads();
+        if (tid < np)
+            for (int c = 0; c < nc; ++c) acc = fmaf(qs[c], ks[tid][c], acc);
+        __syncthreads();
+    }
+    if (tid < np) qkt[(size_t)r * S + j0 + tid] = acc / sqrtf((float)d);
+}
+
+// one CTA per row: p_j = expf(x_j - max) * (1.f / sum) for j < L, zeros up to S
+__global__ void __launch_bounds__(256)
+softmax_lengths_unfused_kernel(float* __restrict__ qkt, const int* __restrict__ lengths, int S) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = min(lengths[r], S);
+    float* row = qkt + (size_t)r * S;
+    float m = -INFINITY;
+    for (int j = tid; j < L; j += 256) m = fmaxf(m, row[j]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float t = red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+        bc = t;
+    }
+    __syncthreads();
+    m = bc;
+    float s = 0.f;
+    for (int j = tid; j < L; j += 256) s += expf(row[j] - m);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        bc = 1.f / t;
+    }
+    __syncthreads();
+    const float inv = bc;
+    for (int j = tid; j < S; j += 256) row[j] = (j < L) ? expf(row[j] - m) * inv : 0.f;
+}
+
+// grid (ceil(d / 256), B), 256 threads: thread = one output column, positions ascending
+__global__ void __launch_bounds__(256)
+softmax_v_unfused_kernel(const float* __restrict__ p, float* const* __restrict__ page_table,
+                         float* __restrict__ out, const int* __restrict__ lengths, int S, int d) {
+    __shared__ float ps[256];
+    __shared__ const float* pages[16];
+    const int r = blockIdx.y, col = blockIdx.x * 256 + threadIdx.x;
+    const int L = lengths[r];
+    float acc = 0.f;
+    for (int j0 = 0; j0 < L; j0 += 256) {
+        const int n = min(256, L - j0);
+        if (threadIdx.x < n) ps[threadIdx.x] = p[(size_t)r * S + j0 + threadIdx.x];
+        if (threadIdx.x < 16 && j0 + threadIdx.x * kPage < L)
+            pages[threadIdx.x] = page_table[(size_t)r * (S / kPage) + j0 / kPage + threadIdx.x];
+        __syncthreads();
+        if (col < d)
+            for (int j = 0; j < n; ++j)
+                acc = fmaf(ps[j], pages[j / kPage][(size_t)(j % kPage) * 3 * d + 2 * d + col], acc);
+        __syncthreads();
+    }
+    if (col < d) out[(size_t)r * d + col] = acc;
+}
+
+int launch_qkt_unfused(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths, float* qkt,
+                       int B, int S, int d) {
+    qkt_unfused_kernel<<<dim3(S / kPage, B), 128, 0, ctx->stream>>>(q, page_table, lengths, qkt, S, d);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_softmax_lengths_unfused(mli_ctx* ctx, float* qkt, const int* lengths, int B, int S) {
+    softmax_lengths_unfused_kernel<<<B, 256, 0, ctx->stream>>>(qkt, lengths, S);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_softmax_v_unfused(mli_ctx* ctx, const float* p, float* const* page_table, float* out,
+                             const int* lengths, int B, int S, int d) {
+    softmax_v_unfused_kernel<<<dim3((d + 255) / 256, B), 256, 0, ctx->stream>>>(p, page_table, out, lengths, S, d);
+    MLI_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace mli

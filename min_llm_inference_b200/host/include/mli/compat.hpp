@@ -16,9 +16,11 @@
 //   ThroughputCounter                                 include/throughput_counter.h:5-18
 //
 // Deliberate differences, all documented in INTEGRATION.md:
-//   * the three unfused attention launchers (qkt / softmax / softmax_v) are one fused call,
-//     launch_fused_decode_attention(); paged_attention() keeps its signature and fills
-//     qkt_output with the softmax probabilities exactly as the reference leaves it;
+//   * paged_attention() runs ONE fused kernel instead of the three unfused launches (qkt / softmax /
+//     softmax_v); it keeps its signature and fills qkt_output with the softmax probabilities exactly
+//     as the reference leaves it.  The three launchers still exist (same signatures, the reference's
+//     summation order) for code and tests written against them; launch_fused_decode_attention() is the
+//     stand-alone fused call;
 //   * the cuBLAS handle arguments are accepted and ignored (there is no cuBLAS in this build);
 //   * the paged engines run on the device scheduler; by default they replay the reference's
 //     stale-length behaviour so finished token lists are identical -- mli::set_fix_stale_lengths(true)
@@ -282,6 +284,13 @@ void launch_get_latest_k_q_v_paged_attention(TensorFloatPoint& page_table, const
                                              const TensorFloat& wk, const TensorFloat& wq,
                                              const TensorFloat& wv, TensorFloat& q_output,
                                              int n_sequence);
+
+// include/kernels/paged_attention.h:37-43, include/kernels/self_attention_inference_optimized.h:21-22
+void launch_qkt_paged_attention(const TensorFloat& q_output, const TensorFloatPoint& page_table,
+                                const TensorInt& lengths, TensorFloat& qkt_output);
+void launch_softmax_in_place_with_lengths(TensorFloat& qkt_output, const TensorInt& lengths);
+void launch_softmax_v_paged_attention(const TensorFloat& softmax_result, const TensorFloatPoint& page_table,
+                                      TensorFloat& attention_result, const TensorInt& lengths);
 
 // fused replacement of launch_qkt_paged_attention + launch_softmax_in_place_with_lengths +
 // launch_softmax_v_paged_attention; softmax_result (may be nullptr) receives the probabilities

@@ -75,6 +75,26 @@ void launch_fused_decode_attention(const TensorFloat& q_output, const TensorFloa
                                           n_sequence, d));
 }
 
+// the reference's three unfused stages (src/kernels/paged_attention.cu:208-345,
+// src/kernels/self_attention_inference_optimized.cu:360-368), same signatures
+void launch_qkt_paged_attention(const TensorFloat& q_output, const TensorFloatPoint& page_table,
+                                const TensorInt& lengths, TensorFloat& qkt_output) {
+    const int B = i(q_output.shape()[0]), d = i(q_output.shape()[1]), S = i(qkt_output.shape()[1]);
+    mli::check(mli_qkt_paged(C(), q_output.data(), page_table.data(), lengths.data(), qkt_output.data(), B, S, d));
+}
+
+void launch_softmax_in_place_with_lengths(TensorFloat& qkt_output, const TensorInt& lengths) {
+    mli::check(mli_softmax_in_place_with_lengths(C(), qkt_output.data(), lengths.data(), i(qkt_output.shape()[0]),
+                                                 i(qkt_output.shape()[1])));
+}
+
+void launch_softmax_v_paged_attention(const TensorFloat& softmax_result, const TensorFloatPoint& page_table,
+                                      TensorFloat& attention_result, const TensorInt& lengths) {
+    const int B = i(softmax_result.shape()[0]), S = i(softmax_result.shape()[1]), d = i(attention_result.shape()[1]);
+    mli::check(mli_softmax_v_paged(C(), softmax_result.data(), page_table.data(), attention_result.data(),
+                                   lengths.data(), B, S, d));
+}
+
 // src/kernels/paged_attention_cublas.cu:260-280
 void paged_attention_with_cublas(TensorFloatPoint& page_table, const TensorInt& lengths,
                                  const TensorFloat& wk, const TensorFloat& wq, const TensorFloat& wv,

@@ -140,6 +140,41 @@ def test_fused_decode_attention(torch_cuda, ctx, ref, B, S, d, V, dist, chunk_pa
         assert np.all(pa[r, L[r]:] == 0.0), "probabilities past L must be zero-filled"
 
 
+@pytest.mark.parametrize("B,S,d,V", SHAPES + [(4, 1024, 1024, 1024)])
+@pytest.mark.parametrize("dist", ["R", "Z"])
+def test_unfused_stages_bit_exact(torch_cuda, ctx, ref, B, S, d, V, dist):
+    """mli_qkt_paged / mli_softmax_in_place_with_lengths / mli_softmax_v_paged (the one-to-one mirrors of
+    the reference's three unfused launchers, tests/paged_attention_kernels_test.cpp:115-169): raw scores
+    and P.V bit-exact (same summation order), softmax within 2e-6 (expf differs), untouched entries kept"""
+    torch = torch_cuda
+    rng = np.random.default_rng(250 + B + d + S)
+    L = make_lengths(rng, B, S)
+    case = H.PagedCase(9, B, S, d, L, dist)
+    pool, tab = case.device(torch)
+    q = H.uniform01(rng, (B, d)) if dist == "R" else \
+        ((rng.random((B, d), dtype=np.float32) - 0.5) * 2.0 * np.sqrt(12.0 / d)).astype(np.float32)
+    dq, dL = dev(torch, q), dev(torch, L)
+    mine = torch.full((B, S), 5.0, device="cuda")
+    theirs = torch.full((B, S), 5.0, device="cuda")
+    ctx.call("mli_qkt_paged", dq, tab, dL, mine, B, S, d)
+    ctx.synchronize()
+    H.check_ref(ref.ref_qkt_paged(H.p(dq), H.p(tab), H.p(dL), H.p(theirs), B, S, d))
+    assert torch.equal(mine, theirs), "raw scores differ from launch_qkt_paged_attention"
+    ctx.call("mli_softmax_in_place_with_lengths", mine, dL, B, S)
+    ctx.synchronize()
+    H.check_ref(ref.ref_softmax_in_place_with_lengths(H.p(theirs), H.p(dL), B, S))
+    pa, pb = mine.cpu().numpy(), theirs.cpu().numpy()
+    assert np.abs(pa - pb).max() < 2e-6
+    for r in range(B):
+        assert np.all(pa[r, L[r]:] == 0.0)
+    out_a = torch.full((B, d), 7.0, device="cuda")
+    out_b = torch.full((B, d), 7.0, device="cuda")
+    ctx.call("mli_softmax_v_paged", theirs, tab, out_a, dL, B, S, d)   # same probabilities on both sides
+    ctx.synchronize()
+    H.check_ref(ref.ref_softmax_v_paged(H.p(theirs), H.p(tab), H.p(out_b), H.p(dL), B, S, d))
+    assert torch.equal(out_a, out_b), "P.V differs from launch_softmax_v_paged_attention"
+
+
 @pytest.mark.parametrize("B,S,d,V", SHAPES)
 @pytest.mark.parametrize("dist", ["R", "Z"])
 def test_decoder_bit_exact(torch_cuda, ctx, ref, B, S, d, V, dist):
