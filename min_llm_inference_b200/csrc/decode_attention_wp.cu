@@ -43,13 +43,25 @@ constexpr int kWpProducerWarp = 15;
 __host__ __device__ constexpr int wp_consumer_warps(int cw) { return cw == 1 ? 15 : (cw == 2 ? 14 : 12); }
 constexpr int kWpMaxStages = 16;
 constexpr int kWpMaxPend = 32;
-constexpr int kWpCtrlInts = 40 + kWpMaxStages + 3 * kWpMaxPend;
+constexpr int kWpCtrlInts = 40 + kWpMaxStages + 4 * kWpMaxPend;
+// rows per entry of the coarse stage prefix (launches with more than kWpFineRows rows, see wp_table_ints)
+constexpr int kWpBlk = 32;
+constexpr int kWpFineRows = 2048;
+// shared-memory ints of the per-row tables: up to kWpFineRows rows keep the exact stage prefix and the
+// lengths of every row ([B + 1] + [B]); beyond that the ring would lose half its depth to them (at 8192
+// rows the two tables are 64 KB: 4 stages instead of 8 at emb_dim 1024, measured 5.8 instead of 7.0 TB/s),
+// so only the prefix of every 32nd row is kept and a segment's row is located with one extra (L2-resident)
+// load of 32 lengths
+__host__ __device__ inline size_t wp_table_ints(int B) {
+    return B <= kWpFineRows ? 2 * (size_t)B + 1 : (size_t)(B + kWpBlk - 1) / kWpBlk + 1;
+}
 
 struct WpSeg {
     int r;        // batch row
     int p0, p1;   // positions [p0, p1) of the row
     int nseg;     // segments the row is cut into (1 = this one produces the final output)
     int pidx;     // partial slot of this segment
+    int start;    // first stage of the row in the flattened stage space
 };
 
 // four consecutive columns (float4 index col) of a K or V row in the ring
@@ -123,8 +135,11 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
     int* pend_r = slice_box + kWpMaxStages;                             // [kWpMaxPend] partial rows to merge
     int* pend_nseg = pend_r + kWpMaxPend;
     int* pend_flag = pend_nseg + kWpMaxPend;
-    int* stage_first = pend_flag + kWpMaxPend;                          // [B + 1]
-    int* len_s = stage_first + B + 1;                                   // [B] the rows' lengths
+    int* pend_start = pend_flag + kWpMaxPend;
+    const bool coarse = B > kWpFineRows;
+    const int NB = (B + kWpBlk - 1) / kWpBlk;                           // coarse: blocks of 32 rows
+    int* stage_first = pend_start + kWpMaxPend;                         // fine [B + 1] / coarse [NB + 1]
+    int* len_s = stage_first + B + 1;                                   // fine only: [B] the rows' lengths
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -171,12 +186,16 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
             if (w < warp) before += t;
         }
         if (r < B) {
-            stage_first[r] = before + v - n;
-            len_s[r] = L;
+            if (!coarse) {
+                stage_first[r] = before + v - n;
+                len_s[r] = L;
+            } else if ((r & (kWpBlk - 1)) == 0) {
+                stage_first[r / kWpBlk] = before + v - n;
+            }
         }
         P += all;
     }
-    if (tid == 0) stage_first[B] = P;
+    if (tid == 0) stage_first[coarse ? NB : B] = P;
     __syncthreads();
     // slices of the flattened stage space: [0, grid) static, then dynamic ones (claimed with an
     // atomic) when the launch is long enough to pay for their merges -- see decode_attention.cu
@@ -199,7 +218,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
         // largest r with stage_first[r] <= cur (empty rows share a start: skipped), by a warp-cooperative
         // 32-ary search: every lane probes one candidate per round (all lanes call next_seg together)
         int lo = 0;
-        for (int n = B; n > 1;) {
+        for (int n = coarse ? NB : B; n > 1;) {
             const int step = (n + 31) >> 5;
             const int idx = lo + lane * step;
             const bool le = (idx < lo + n) && (stage_first[idx] <= cur);
@@ -208,11 +227,35 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
             lo += k * step;
             n = min(step, end - lo);
         }
-        const int start = stage_first[lo], n_st = stage_first[lo + 1] - start;
+        int start, n_st, len;
+        if (!coarse) {
+            start = stage_first[lo];
+            n_st = stage_first[lo + 1] - start;
+            len = len_s[lo];
+        } else {
+            // lo = the block of 32 rows that holds stage `cur`; lane i takes row 32 * lo + i
+            const int row = lo * kWpBlk + lane;
+            const int Lr = (row < B) ? __ldg(lengths + row) : 0;
+            const int n = (Lr + G - 1) / G;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int first = stage_first[lo] + incl - n;
+            const unsigned hit = __ballot_sync(0xffffffffu, n > 0 && first <= cur && cur < first + n);
+            const int k = __ffs(hit) - 1;   // exactly one lane: cur < g1 <= P lies inside some row
+            start = __shfl_sync(0xffffffffu, first, k);
+            n_st = __shfl_sync(0xffffffffu, n, k);
+            len = __shfl_sync(0xffffffffu, Lr, k);
+            lo = lo * kWpBlk + k;
+        }
         const int st1 = min(g1 - start, n_st);
         sg.r = lo;
+        sg.start = start;
         sg.p0 = (cur - start) * G;
-        sg.p1 = min(st1 * G, len_s[lo]);   // only the row's last stage can be partial
+        sg.p1 = min(st1 * G, len);   // only the row's last stage can be partial
         sg.nseg = slice_of(start + n_st - 1) - slice_of(start) + 1;
         sg.pidx = 2 * slice + (cur == g0 ? 0 : 1);
         cur = start + st1;
@@ -305,7 +348,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
     const float sqrt_d = sqrtf((float)d);
     // empty rows produce zeros (the reference stores result = 0, paged_attention.cu:289,:323)
     for (int r = blockIdx.x; r < B; r += gridDim.x) {
-        if (stage_first[r + 1] != stage_first[r]) continue;
+        if (coarse ? (__ldg(lengths + r) > 0) : (stage_first[r + 1] != stage_first[r])) continue;
         for (int col = tid; col < d4; col += kWpConsumerThreads)
             reinterpret_cast<float4*>(out + (size_t)r * d)[col] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -329,7 +372,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
             if (!pend_flag[pi]) continue;
             const int r = pend_r[pi], nseg = pend_nseg[pi];
             if (dbg != nullptr && tid == 0) dbg[(size_t)blockIdx.x * 16 + 11] += ((long long)nseg << 32) | 1;
-            const int start = stage_first[r];
+            const int start = pend_start[pi];
             const int b_first = slice_of(start);
             // segment k of the row lives in slice b_first + k: its head slot, except that the row's
             // first segment is its slice's tail slot unless the row opens that slice
@@ -417,7 +460,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
                 qv[i] = reinterpret_cast<const float4*>(q + (size_t)sg.r * d)[cbase + 32 * i];
         }
         while (have) {
-            const int r = sg.r, p0 = sg.p0, p1 = sg.p1;
+            const int r = sg.r, p0 = sg.p0, p1 = sg.p1, row_start = sg.start;
             float4 acc[NCW];
 #pragma unroll
             for (int i = 0; i < NCW; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -547,6 +590,7 @@ decode_attention_wp_kernel(const float* __restrict__ q, float* const* __restrict
                         part_ml[2 * pidx + 1] = Lsum;
                         pend_r[n_pend] = r;
                         pend_nseg[n_pend] = nseg;
+                        pend_start[n_pend] = row_start;
                     }
                     ++n_pend;
                 }
@@ -576,7 +620,7 @@ size_t wp_smem_bytes(int B, int d, int CW, int G, int nstage, bool kvb) {
     const int PW = wp_consumer_warps(CW) / CW;
     const size_t rowb = kvb ? 4 * (size_t)d : 8 * (size_t)d;
     return (size_t)nstage * G * rowb + sizeof(float) * ((size_t)PW * d + 2 * PW + 2 * PW * CW) +
-           (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + 2 * (size_t)B + 1) + 128;
+           (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + wp_table_ints(B)) + 128;
 }
 
 template <int NCW, int CW, bool KVB>
@@ -616,7 +660,7 @@ bool wp_plan(int B, int d, bool kvb, int* G_out, int* nstage_out) {
     int G = (int)std::max<size_t>(1, (16 * 1024) / rowb);
     if (G > 32) G = 32;
     const size_t fixed = sizeof(float) * ((size_t)PW * d + 2 * PW + 2 * PW * CW) +
-                         (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + 2 * (size_t)B + 1) + 128;
+                         (2 * kWpMaxStages + 4) * sizeof(uint64_t) + sizeof(int) * (kWpCtrlInts + wp_table_ints(B)) + 128;
     if (fixed >= 226 * 1024) return false;
     const size_t budget = 226 * 1024 - fixed;
     int nstage = kWpMaxStages;   // a power of two: the kernel masks instead of dividing

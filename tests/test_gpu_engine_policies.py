@@ -287,3 +287,47 @@ def test_attention_soak_random_lengths(torch_cuda, ctx, kernel):
     finally:
         ctx.set_option(mli.OPT_ATTN_KERNEL, 0)
         ctx.set_option(mli.OPT_ATTN_MIN_DYN, 4096)
+
+
+@pytest.mark.parametrize("B,min_dyn", [(2049, 4096), (5000, 4096), (8192, 1), (3333, 1)])
+def test_attention_many_rows_coarse_row_table(torch_cuda, ctx, B, min_dyn):
+    """more than 2048 rows: the warp-per-position kernel keeps only every 32nd row's stage prefix in shared
+    memory and locates rows with a second-level lookup; whole blocks of empty rows, a ragged tail block and
+    dynamic slices are covered"""
+    torch = torch_cuda
+    S, d = 128, 128
+    rng = np.random.default_rng(B)
+    L = rng.integers(0, S, size=B).astype(np.int32)
+    L[rng.random(B) < 0.3] = 0
+    L[64:160] = 0            # three whole 32-row blocks without work
+    L[-5:] = [S - 1, 0, 1, 0, 17]
+    if B > 4000:
+        L[2100:4000] = 0     # a long empty stretch
+    # rows share a handful of pages (content is irrelevant to the row lookup, the pool stays small)
+    n_pages = 64
+    pool = (torch.rand((n_pages, 16 * 3 * d), device="cuda") - 0.5) * 2.0
+    W = S // 16
+    pid = rng.integers(0, n_pages, size=(B, W))
+    tab = torch.from_numpy((pool.data_ptr() + pid.astype(np.int64) * (16 * 3 * d * 4))).cuda()
+    q = torch.rand((B, d), device="cuda") - 0.5
+    out = torch.full((B, d), 9.0, device="cuda")
+    dL = torch.from_numpy(L).cuda()
+    ctx.set_option(mli.OPT_ATTN_KERNEL, 2)
+    ctx.set_option(mli.OPT_ATTN_MIN_DYN, min_dyn)
+    try:
+        ctx.call("mli_decode_attention_paged", q, tab, dL, out, None, B, S, d)
+        ctx.synchronize()
+    finally:
+        ctx.set_option(mli.OPT_ATTN_KERNEL, 0)
+        ctx.set_option(mli.OPT_ATTN_MIN_DYN, 4096)
+    pages = pool.view(n_pages, 16, 3, d).double()
+    pidt = torch.from_numpy(pid).cuda()
+    K = pages[pidt, :, 1, :].reshape(B, S, d)
+    V = pages[pidt, :, 2, :].reshape(B, S, d)
+    sc = torch.einsum("bd,bsd->bs", q.double(), K) / np.sqrt(np.float64(d))
+    mask = torch.arange(S, device="cuda")[None, :] < dL[:, None]
+    p = torch.nan_to_num(torch.softmax(sc.masked_fill(~mask, float("-inf")), dim=1), nan=0.0)
+    want = torch.einsum("bs,bsd->bd", p, V)
+    err = float((out.double() - want).abs().max() / want.abs().max())
+    assert err < 1e-4, f"rel err {err:.2e}"
+    assert not out[dL == 0].any(), "empty rows must produce zeros"

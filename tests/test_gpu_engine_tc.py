@@ -83,7 +83,8 @@ def test_bench_workload_tc_equals_exact_mode(torch_cuda, tc):
     """the bench job (BASELINE configs[1]) in tensor-core mode produces the token lists of the
     exact-order mode, request by request, with identical scheduler counters"""
     torch = torch_cuda
-    from bench import WORKLOAD as wl
+    from bench import WORKLOADS
+    wl = WORKLOADS["c2a"]
     cfg = dict(B=wl["B"], S=wl["S"], d=wl["d"], V=wl["V"], n_blocks=wl["n_blocks"], R=wl["R"])
     w = H.make_weights(1001, wl["d"], wl["V"], wl["S"], "Z")
     offs, toks = H.make_prompts(2002, wl["n_req"], wl["lo"], wl["hi"])

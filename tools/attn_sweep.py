@@ -26,6 +26,9 @@ SHAPES = [
     ("d=2048 mid", 512, 2048, 1024, (1, 1023), 1.0),
     ("d=4096 short", 128, 4096, 2048, (1, 2047), 1.0),
     ("configs[3]", 128, 4096, 32768, (12000, 20000), 1.0),
+    ("B=2048 d=1024", 2048, 1024, 2304, (64, 2176), 1.0),
+    ("B=4096 d=1024", 4096, 1024, 2304, (64, 2176), 1.0),
+    ("configs[4] step (N=1)", 8192, 1024, 2304, (64, 2176), 1.0),
 ]
 
 

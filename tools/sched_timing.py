@@ -14,7 +14,8 @@ sys.path.insert(0, str(REPO))
 sys.path.insert(0, str(REPO / "tests"))
 import harness as H  # noqa: E402
 import min_llm_inference_b200 as mli  # noqa: E402
-from bench import WORKLOAD  # noqa: E402
+from bench import WORKLOADS  # noqa: E402
+WORKLOAD = WORKLOADS["c2a"]
 
 PHASES = ["own state + ring window + queue head fetched (before the wait)", "dependency wait (decoder tail)",
           "lengths loaded", "phase 1: decoder results, retire", "phase 2: free pages, compact used list",

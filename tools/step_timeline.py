@@ -18,7 +18,8 @@ sys.path.insert(0, str(REPO))
 sys.path.insert(0, str(REPO / "tests"))
 import harness as H  # noqa: E402
 import min_llm_inference_b200 as mli  # noqa: E402
-from bench import WORKLOAD  # noqa: E402
+from bench import WORKLOADS  # noqa: E402
+WORKLOAD = WORKLOADS["c2a"]
 
 SLOTS = ["sched_step", "encoder", "QKV+prefill GEMM", "decode attention", "logits GEMM", "decoder"]
 
