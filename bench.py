@@ -271,6 +271,14 @@ def reference_cuda_pairs(ctx, torch):
         return None
     ref = H.load_ref()
     shapes = {
+        # BASELINE configs[0]: the NON-paged engine (start_inference_engine, src/inferencer.cpp:11-41; no Q1 quirk
+        # there), ours = the same device engine with a pool that cannot run dry (what the C++ drop-in
+        # start_inference_engine runs, host/src/engine.cpp)
+        "configs0_C1_dense": dict(B=32, S=256, d=256, V=1024, n_blocks=32 * 16, n_req=96, lo=1, hi=128, dist="Z",
+                                  eof=1.0001, dense=True),
+        # the non-paged mode at a larger shape
+        "dense_larger_shape": dict(B=128, S=512, d=1024, V=1024, n_blocks=128 * 32, n_req=256, lo=32, hi=384, dist="Z",
+                                   eof=1.0001, dense=True),
         "configs1_C2a": dict(B=256, S=128, d=1024, V=1024, n_blocks=1024, n_req=512, lo=1, hi=64, dist="Z", eof=1.0001),
         "paged_for_profile_C2b": dict(B=1024, S=128, d=2048, V=1024, n_blocks=4096, n_req=2048, lo=1, hi=64, dist="R",
                                       eof=1.0001),
@@ -281,7 +289,9 @@ def reference_cuda_pairs(ctx, torch):
         offs, toks = H.make_prompts(SEED_P, c["n_req"], c["lo"], c["hi"])
         n_req, S = c["n_req"], c["S"]
         res = {"shape": {k: c[k] for k in ("B", "S", "d", "V", "n_blocks", "n_req", "lo", "hi", "dist")}}
-        for name, variant, runs in (("warp_tiling_cublas", 1, 5), ("naive", 0, 3)):
+        dense = c.get("dense", False)
+        for name, variant, runs in ((("dense_engine", -1, 5),) if dense else
+                                    (("warp_tiling_cublas", 1, 5), ("naive", 0, 3))):
             ids = np.zeros(n_req, np.int32)
             fo = np.zeros(n_req + 1, np.int32)
             ft = np.zeros(n_req * S, np.int32)
@@ -290,10 +300,16 @@ def reference_cuda_pairs(ctx, torch):
             for i in range(runs + 1):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                H.check_ref(ref.ref_run_paged_engine(variant, c["B"], S, c["d"], c["V"], c["n_blocks"], 1,
-                                                     H.p(w["emb"]), H.p(w["pos"]), H.p(w["wk"]), H.p(w["wq"]),
-                                                     H.p(w["wv"]), n_req, H.p(offs), H.p(toks), H.p(ids),
-                                                     H.p(fo), H.p(ft), C.byref(nf), C.byref(sec)))
+                if dense:
+                    H.check_ref(ref.ref_run_dense_engine(c["B"], S, c["d"], c["V"], H.p(w["emb"]), H.p(w["pos"]),
+                                                         H.p(w["wk"]), H.p(w["wq"]), H.p(w["wv"]), n_req, H.p(offs),
+                                                         H.p(toks), H.p(ids), H.p(fo), H.p(ft), C.byref(nf),
+                                                         C.byref(sec)))
+                else:
+                    H.check_ref(ref.ref_run_paged_engine(variant, c["B"], S, c["d"], c["V"], c["n_blocks"], 1,
+                                                         H.p(w["emb"]), H.p(w["pos"]), H.p(w["wk"]), H.p(w["wq"]),
+                                                         H.p(w["wv"]), n_req, H.p(offs), H.p(toks), H.p(ids),
+                                                         H.p(fo), H.p(ft), C.byref(nf), C.byref(sec)))
                 e1.record()
                 torch.cuda.synchronize()
                 gen = int(fo[nf.value]) - int(offs[-1])
@@ -304,7 +320,8 @@ def reference_cuda_pairs(ctx, torch):
                          "tok_s_best_wall": gen / min(walls), "tok_s_worst_wall": gen / max(walls),
                          "tok_s_median_device_events": gen / float(np.median(evs)), "runs": runs}
         dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
-        for name, compat in (("ours_same_work_q1_replayed", 1), ("ours_corrected_lengths", 0)):
+        for name, compat in ((("ours_device_engine", 0),) if dense else
+                             (("ours_same_work_q1_replayed", 1), ("ours_corrected_lengths", 0))):
             ec = mli.EngineCfg(c["B"], S, c["d"], c["V"], c["n_blocks"], 1, compat, n_req, None)
             eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
             walls, gen = [], 0
@@ -320,8 +337,12 @@ def reference_cuda_pairs(ctx, torch):
             eng.close()
             res[name] = {"tokens": int(gen), "tok_s_median_wall": gen / float(np.median(walls)), "runs": 5,
                          "timed": "wall clock: host prompts in, finished token lists out (the reference's metric)"}
-        res["speedup_same_work_vs_warp_tiling_cublas"] = (res["ours_same_work_q1_replayed"]["tok_s_median_wall"] /
-                                                          res["warp_tiling_cublas"]["tok_s_median_wall"])
+        if dense:
+            res["speedup_vs_reference_dense_engine"] = (res["ours_device_engine"]["tok_s_median_wall"] /
+                                                        res["dense_engine"]["tok_s_median_wall"])
+        else:
+            res["speedup_same_work_vs_warp_tiling_cublas"] = (res["ours_same_work_q1_replayed"]["tok_s_median_wall"] /
+                                                              res["warp_tiling_cublas"]["tok_s_median_wall"])
         out[key] = res
     out["note"] = ("reference engines replay quirk Q1 (stale lengths): rows attend over at most the prompt length and "
                    "re-emit their first token until n_sequence; 'ours_same_work' replays it too (identical token lists "
@@ -576,7 +597,9 @@ def main():
             if not args.no_large:
                 # the same engine at the other BASELINE configurations, at their named shapes
                 sys.path.insert(0, str(REPO / "tools"))
-                for key, preset, kvb in (("engine_configs1", "c2a", 0), ("engine_configs2", "c3", 0),
+                for key, preset, kvb in (("engine_configs1", "c2a", 0), ("engine_configs1_admission_throttle", "c2a_pf", 0),
+                                         ("engine_configs1_four_rounds", "c2a_r4", 0),
+                                         ("engine_configs2", "c3", 0),
                                          ("engine_configs3", "c4", 0), ("engine_configs2_compact_kv", "c3", 1)):
                     try:
                         import run_config

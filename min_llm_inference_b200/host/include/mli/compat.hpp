@@ -357,6 +357,10 @@ public:
                        size_t input_dim, size_t n_sequence);
     void forward(const TensorFloat& inp_embedding, const TensorInt& lengths,
                  const TensorInt& new_batch_idx, TensorFloat& attention_result, int n_new_items);
+    // extension: the device engine reads the owned weights
+    const TensorFloat& wk() const { return wk_; }
+    const TensorFloat& wq() const { return wq_; }
+    const TensorFloat& wv() const { return wv_; }
 
 private:
     TensorFloat wk_, wq_, wv_;
@@ -450,6 +454,8 @@ public:
     void forward(const TensorInt& inp, TensorInt& lengths, const TensorInt& new_item_indices,
                  TensorInt& decoder_result, int n_new_items, const TensorFloat& emb_table,
                  const TensorFloat& pos_emb_table);
+    const SelfAttentionLayer& attention_layer() const { return attention_layer_; }  // extension
+    size_t emb_dim() const { return emb_dim_; }
 
 private:
     SelfAttentionLayer attention_layer_;

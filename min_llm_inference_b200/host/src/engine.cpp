@@ -1,9 +1,7 @@
 // engine.cpp -- the three engine loops of include/inferencer.h.
 //
-// start_inference_engine (non-paged, config C1) keeps the reference's host loop
-// (src/inferencer.cpp:11-41) over InferenceModel::forward -- it is launch-bound and tiny.
-//
-// The two paged engines (src/inferencer.cpp:43-133) hand the whole job to the on-device engine
+// All three (the non-paged start_inference_engine, src/inferencer.cpp:11-41, and the two paged
+// engines, :43-133) hand the whole job to the on-device engine
 // (mli_engine_*): requests are uploaded once, the scheduler / page manager run on the GPU, and the
 // finished token lists come back in finish order.  The caller-visible post-state matches the
 // reference: item_storage.finished holds every request in finish order, the new-item queue and
@@ -15,9 +13,16 @@
 
 #include "mli/compat.hpp"
 
-void start_inference_engine(const TensorFloat& emb_table, const TensorFloat& pos_table,
-                            ItemStorage& item_storage, ProcessingStorage& processing_storage,
-                            InferenceModel& inference_model, size_t n_batch_size, size_t n_sequence) {
+namespace {
+void run_device_job(const TensorFloat& emb_table, const TensorFloat& pos_table, ItemStorage& item_storage,
+                    float* slab, int n_blocks, const TensorFloat& wk, const TensorFloat& wq, const TensorFloat& wv,
+                    size_t n_batch, size_t n_sequence, size_t emb_dim, int n_forward_rounds, bool compat);
+
+// the reference's host loop (src/inferencer.cpp:11-41) over InferenceModel::forward, kept for
+// MLI_DENSE_HOST_LOOP=1: one blocking D2H + up to three blocking H2D copies per generated token
+void dense_host_loop(const TensorFloat& emb_table, const TensorFloat& pos_table, ItemStorage& item_storage,
+                     ProcessingStorage& processing_storage, InferenceModel& inference_model, size_t n_batch_size,
+                     size_t n_sequence) {
     std::vector<int> free_rows(n_batch_size);
     for (size_t r = 0; r < n_batch_size; ++r) free_rows[r] = static_cast<int>(r);
     TensorInt inp_device({n_batch_size, n_sequence}, DeviceType::DEVICE);
@@ -41,6 +46,32 @@ void start_inference_engine(const TensorFloat& emb_table, const TensorFloat& pos
         n_new = insert_new_items(free_rows, inp_device, inp_host, lengths_device, lengths_host,
                                  idx_device, idx_host, item_storage, processing_storage);
     }
+}
+}  // namespace
+
+// start_inference_engine (non-paged, BASELINE configs[0]; src/inferencer.cpp:11-41).  The reference
+// keeps dense K^T / V caches of n_batch * n_sequence * emb_dim floats inside the model; they are not
+// visible at this level, so the B200 build runs the job on the SAME on-device engine as the paged
+// entry points, with a private pool that can never run dry (n_batch * n_sequence / 16 pages: every row
+// can reach n_sequence) and corrected lengths -- the non-paged scheduler (item_storage.cpp:141-180) is the
+// paged one without page pressure: queue heads go to free rows in row order, finished requests are
+// reported in row order.  Tokens and finish order equal the reference's (tests/test_gpu_dropin.py,
+// tests/test_gpu_forward_engine.py P2).  MLI_DENSE_HOST_LOOP=1 keeps the reference's host loop over the
+// dense stage kernels instead.
+void start_inference_engine(const TensorFloat& emb_table, const TensorFloat& pos_table,
+                            ItemStorage& item_storage, ProcessingStorage& processing_storage,
+                            InferenceModel& inference_model, size_t n_batch_size, size_t n_sequence) {
+    const char* host_loop = std::getenv("MLI_DENSE_HOST_LOOP");
+    if ((host_loop && host_loop[0] == '1') || n_sequence % PAGE_BLOCK_SIZE != 0) {
+        dense_host_loop(emb_table, pos_table, item_storage, processing_storage, inference_model, n_batch_size,
+                        n_sequence);
+        return;
+    }
+    const SelfAttentionLayer& layer = inference_model.attention_layer();
+    const int W = static_cast<int>(n_sequence) / PAGE_BLOCK_SIZE;
+    const int n_blocks = static_cast<int>(n_batch_size) * std::max(W, DEFAULT_INIT_NUM_BLOCKS);
+    run_device_job(emb_table, pos_table, item_storage, nullptr, n_blocks, layer.wk(), layer.wq(), layer.wv(),
+                   n_batch_size, n_sequence, inference_model.emb_dim(), 1, false);
 }
 
 namespace mli {
@@ -227,6 +258,17 @@ void run_paged_job(const TensorFloat& emb_table, const TensorFloat& pos_table, I
                               n_forward_rounds, mli::num_gpus());
         return;
     }
+    if (pool.free_blocks_size() != pool.total_blocks())
+        throw std::runtime_error("paged engine: memory_block_manager must start with every block free");
+    (void)processing_storage;  // nothing is left processing when the job returns
+    // the engine carves its pages from the caller's slab
+    run_device_job(emb_table, pos_table, item_storage, pool.slab(), pool.total_blocks(), wk, wq, wv, n_batch,
+                   n_sequence, emb_dim, n_forward_rounds, !mli::fix_stale_lengths());
+}
+
+void run_device_job(const TensorFloat& emb_table, const TensorFloat& pos_table, ItemStorage& item_storage,
+                    float* slab, int n_blocks, const TensorFloat& wk, const TensorFloat& wq, const TensorFloat& wv,
+                    size_t n_batch, size_t n_sequence, size_t emb_dim, int n_forward_rounds, bool compat) {
     const auto t0 = std::chrono::high_resolution_clock::now();
     // drain the queue: request k of the job is the k-th queued item (ids are the caller's)
     std::vector<IdTokensPair> reqs = item_storage.pop_new_items(item_storage.new_count());
@@ -236,19 +278,17 @@ void run_paged_job(const TensorFloat& emb_table, const TensorFloat& pos_table, I
         tokens.insert(tokens.end(), reqs[k].second.begin(), reqs[k].second.end());
         offsets[k + 1] = static_cast<int>(tokens.size());
     }
-    if (pool.free_blocks_size() != pool.total_blocks())
-        throw std::runtime_error("paged engine: memory_block_manager must start with every block free");
 
     mli_engine_cfg cfg{};
     cfg.n_batch = static_cast<int>(n_batch);
     cfg.n_sequence = static_cast<int>(n_sequence);
     cfg.emb_dim = static_cast<int>(emb_dim);
     cfg.n_vocab = static_cast<int>(emb_table.shape()[0]);
-    cfg.n_blocks = pool.total_blocks();
+    cfg.n_blocks = n_blocks;
     cfg.n_forward_rounds = n_forward_rounds;
-    cfg.compat_stale_lengths = mli::fix_stale_lengths() ? 0 : 1;
+    cfg.compat_stale_lengths = compat ? 1 : 0;
     cfg.max_requests = n_req > 0 ? n_req : 1;
-    cfg.page_pool = pool.slab();  // the engine carves its pages from the caller's slab
+    cfg.page_pool = slab;  // nullptr: the engine allocates its own pool
 
     mli_engine* engine = nullptr;
     mli::check(mli_engine_create(mli::host_context(), &cfg, emb_table.data(), pos_table.data(),
@@ -272,7 +312,6 @@ void run_paged_job(const TensorFloat& emb_table, const TensorFloat& pos_table, I
         item_storage.add_finished_item(IdTokensPair(
             reqs[q].first, std::vector<int>(fin_toks.begin() + fin_offs[k], fin_toks.begin() + fin_offs[k + 1])));
     }
-    (void)processing_storage;  // nothing is left processing when the job returns
     const auto t1 = std::chrono::high_resolution_clock::now();
     ThroughputCounter& counter = get_global_throughput_counter();
     counter.add_job(stats.generated_tokens, std::chrono::duration<double>(t1 - t0).count());
