@@ -219,3 +219,26 @@ def test_oracle_against_reference_cuda_golden(path):
             fo, ft = g[f"{name}_offsets"], g[f"{name}_tokens"]
             for k, rid in enumerate(order):
                 assert np.array_equal(res[int(rid)], ft[fo[k]:fo[k + 1]])
+
+
+def test_oracle_policy_flags():
+    """the two opt-in scheduling policies the product engine adds (mli_engine_cfg.max_new_tokens /
+    max_prefill_positions) as restated in the oracle: the token cap truncates every request's generation,
+    the admission throttle changes WHEN requests are admitted but -- with corrected lengths -- never a token"""
+    cfg = dict(B=6, S=64, d=32, V=1024, n_blocks=40, R=1)
+    w = H.make_weights(11, cfg["d"], cfg["V"], cfg["S"], "Z")
+    offs, toks = H.make_prompts(13, 15, 3, 30)
+    plen = np.diff(offs)
+    rc, base, order, st = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1)
+    assert rc == 0 and st.n_finished == 15
+    rc, capped, _, st_c = H.run_oracle_engine("paged", dict(cfg, max_new=5), w, offs, toks, fix=1)
+    assert rc == 0 and st_c.n_finished == 15
+    for i in range(15):
+        assert len(capped[i]) - plen[i] <= 5
+        assert np.array_equal(capped[i], base[i][:len(capped[i])])
+    assert st_c.steps < st.steps
+    rc, thr, _, st_t = H.run_oracle_engine("paged", dict(cfg, max_prefill=24), w, offs, toks, fix=1)
+    assert rc == 0 and st_t.n_finished == 15
+    for i in range(15):
+        assert np.array_equal(thr[i], base[i])
+    assert st_t.steps >= st.steps      # admissions are spread over more iterations
