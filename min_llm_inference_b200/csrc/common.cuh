@@ -240,6 +240,7 @@ enum WsSlot {
     WS_QOUT,           // q_output when the caller passes NULL
     WS_ATTN_OUT,       // attention_result when the caller passes NULL
     WS_QKT,            // dense-path score scratch
+    WS_TC_CTR,         // tile counters of the persistent tcgen05 GEMM launches (zero between launches)
     WS_NUM_SLOTS
 };
 }  // namespace mli

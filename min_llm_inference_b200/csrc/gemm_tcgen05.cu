@@ -171,6 +171,11 @@ struct TcArgs {
     long long* dbg;        // optional phase stamps
     unsigned long long* trace;  // optional step timeline
     int trace_slot;
+    // persistent launches (bulk plans: split == 1, no deferred reduce): grid = one CTA per SM, work items
+    // (feature tile, activation tile) handed out by an atomic counter -- see tc_item()
+    int dyn;               // 1 = persistent / dynamic items
+    int m_tiles;           // feature tiles of the operand
+    int* ctr;              // [2]: next item, CTAs finished (both back at zero when the launch ends)
 };
 
 // optional phase stamps (clock64 of one thread per role) for tools/gemm_timing.py: [cta][8]
@@ -229,6 +234,43 @@ __device__ __forceinline__ int tc_n_valid(const TcArgs& args) {
         n = min(n, args.counts[0]);
     }
     return n;
+}
+
+// Persistent launches: the work of a launch is the list of (activation tile, feature tile) pairs that have
+// something to compute, feature tile fastest (the CTAs working at the same time share the activation rows
+// through L2).  Activation tiles that hold active rows (STEP: the first ceil(pad / bn) tiles) need every
+// feature tile; tiles of prefill positions need K and V features only (no q for prefill positions), so a
+// launch that is mostly prefill keeps every SM busy instead of idling the third that owns q features.
+struct TcItems {
+    int a_tiles;   // activation tiles that need all feature tiles
+    int kv_tiles;  // feature tiles a pure prefill tile needs
+    int n_items;
+};
+__device__ __forceinline__ TcItems tc_items(const TcArgs& args, int n_valid) {
+    TcItems t;
+    const int n_tiles = (n_valid + args.bn - 1) / args.bn;
+    if (args.mode == TC_STEP) {
+        const int pad = (args.counts[0] + 15) & ~15;
+        t.a_tiles = min(n_tiles, (pad + args.bn - 1) / args.bn);
+        t.kv_tiles = 2 * (args.d / kBM);
+    } else {
+        t.a_tiles = n_tiles;
+        t.kv_tiles = args.m_tiles;
+    }
+    t.n_items = t.a_tiles * args.m_tiles + (n_tiles - t.a_tiles) * t.kv_tiles;
+    return t;
+}
+__device__ __forceinline__ void tc_item(const TcArgs& args, const TcItems& t, int item, int* mt, int* nt) {
+    const int full = t.a_tiles * args.m_tiles;
+    if (item < full) {
+        *nt = item / args.m_tiles;
+        *mt = item % args.m_tiles;
+    } else {
+        const int u = item - full;
+        *nt = t.a_tiles + u / t.kv_tiles;
+        const int k = u % t.kv_tiles, per = args.d / kBM;
+        *mt = (k < per) ? k : k + per;   // K features, then V features ([Wk^T; Wq^T; Wv^T]: skip the q block)
+    }
 }
 
 __device__ __forceinline__ RowIO row_io(const TcArgs& args, int n, int n_valid, int mat, int f0) {
@@ -296,6 +338,7 @@ __device__ __forceinline__ RowIO row_io(const TcArgs& args, int n, int n_valid, 
 //               UMMA 128B-swizzled K-major layout -- no staging pass through HBM; afterwards the
 //               same warps drain TMEM (tcgen05.ld) into the partial tile / the destination rows
 // ---------------------------------------------------------------------------------------------
+template <bool kDyn>
 __global__ void __launch_bounds__(kTcThreadsV2, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    TcArgs args) {
@@ -324,19 +367,43 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // which features does this CTA produce?
     // LATEST: operand rows are [Wk^T; Wq^T; Wv^T] -> mat 0 = K, 1 = q, 2 = V
     // PREFILL: operand rows are [Wk^T; Wv^T]        -> mat 0 = K, 1 -> 2 = V
-    const int m0 = blockIdx.x * kBM;
+    constexpr bool dyn = kDyn;   // persistent launch with dynamic work items (args.dyn), see tc_items()
+    __shared__ int s_next_item[2];
+    int m0 = blockIdx.x * kBM;
     int mat = 0, f0 = m0;
-    if (args.mode != TC_LOGITS) {
-        mat = m0 / args.d;
-        f0 = m0 % args.d;
-        if (args.mode == TC_PREFILL && mat == 1) mat = 2;
+    auto set_features = [&](int m_tile) {
+        m0 = m_tile * kBM;
+        mat = 0;
+        f0 = m0;
+        if (args.mode != TC_LOGITS) {
+            mat = m0 / args.d;
+            f0 = m0 % args.d;
+            if (args.mode == TC_PREFILL && mat == 1) mat = 2;
+        }
+    };
+    set_features((int)blockIdx.x);
+    // persistent launch: this CTA's first item is its own index (known without looking at the counter, so
+    // the weight tiles of that item can be requested before the dependency wait); the scheduler's counts are
+    // final long before this kernel can start (see below)
+    // (the item geometry lives in shared memory, not in registers: the converter warps are at the register limit)
+    __shared__ TcItems s_items;
+    int item = (int)blockIdx.x, nt_dyn = 0, n_items = 0;
+    if (dyn) {
+        const TcItems items = tc_items(args, tc_n_valid(args));
+        if (tid == 0) s_items = items;   // published by the set-up barrier below
+        n_items = items.n_items;
+        if (item < n_items) {
+            int mt;
+            tc_item(args, items, item, &mt, &nt_dyn);
+            set_features(mt);
+        }
     }
 
     // The extra activation-tile walkers of a step launch (blockIdx.y >= 1) only ever see tiles past the
     // first; when all active rows fit the first tile those hold prefill positions only, which need no
     // q: their q-feature clusters leave before allocating anything.  (The scheduler's counts are final
     // long before this kernel can start, so they may be read ahead of griddepcontrol.wait.)
-    if (args.mode == TC_STEP && blockIdx.y >= 1 && mat == 1 && ((args.counts[0] + 15) & ~15) <= bn) return;
+    if (!dyn && args.mode == TC_STEP && blockIdx.y >= 1 && mat == 1 && ((args.counts[0] + 15) & ~15) <= bn) return;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi);
         prefetch_tmap(&map_a_lo);
@@ -363,7 +430,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int kb_per_acc = (kb_per + args.n_acc - 1) / args.n_acc;
     // The weights are static: the producer starts filling the pipeline with weight tiles right away,
     // before this kernel is allowed to look at anything its predecessor wrote.
-    const int n_pre = min(nst, kb_per);
+    const int n_pre = (dyn && item >= n_items) ? 0 : min(nst, kb_per);
     const uint64_t w_policy = l2_policy_evict_last();
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < n_pre; ++i) {
@@ -382,7 +449,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
     uint32_t it = 0;        // pipeline counter (runs on across tiles; identical in every role)
     uint32_t tile_iter = 0;   // tiles this CTA really processed
-    for (int nt = blockIdx.y; nt * bn < n_valid; nt += gridDim.y) {
+    for (int nt = dyn ? nt_dyn : (int)blockIdx.y;;) {
+        if (dyn ? (item >= n_items) : (nt * bn >= n_valid)) break;
+        // persistent launch: claim the NEXT item now; the barrier below publishes it (two slots: a thread may
+        // still be reading this iteration's slot when thread 0 claims the one after)
+        // (a persistent launch never skips a tile, so tile_iter counts the loop iterations)
+        if (dyn && tid == 0) s_next_item[tile_iter & 1] = (int)gridDim.x + atomicAdd(&args.ctr[0], 1);
         const int n0 = nt * bn;
         const int n_eff = min(bn, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
         // ---- row tables of the tile ----
@@ -396,7 +468,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         // A tile none of whose rows wants this CTA's features (q features over a tile of prefill
         // positions) is skipped.  The decision depends only on (feature tile, activation tile), so
         // it is the same in every CTA of the cluster.
-        if (!__syncthreads_or(live)) continue;
+        const bool any_live = __syncthreads_or(live);
+        // static launches skip a tile nobody wants; a persistent launch only lists tiles with work (a tile of
+        // prefill granules that all lie past their row's length is computed for nothing, which is rare and
+        // keeps the weight tiles requested ahead of the wait valid)
+        if (!any_live && !dyn) {
+            nt += gridDim.y;
+            continue;
+        }
 
         if (warp == 0) {
             // ===================== TMA producer (weights) =====================
@@ -583,6 +662,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         tc_fence_after();
         it += (uint32_t)kb_per;
         ++tile_iter;
+        if (dyn) {
+            // (the slot of the iteration that just ended; it is next written two iterations from now)
+            item = s_next_item[(tile_iter - 1) & 1];
+            if (item < n_items) {
+                int mt;
+                tc_item(args, s_items, item, &mt, &nt);
+                set_features(mt);
+            }
+        } else {
+            nt += gridDim.y;
+        }
+    }
+    if (dyn && tid == 0) {
+        // the last CTA out re-arms both counters for the next launch
+        __threadfence();
+        if (atomicAdd(&args.ctr[1], 1) == (int)gridDim.x - 1) {
+            args.ctr[0] = 0;
+            args.ctr[1] = 0;
+            __threadfence();
+        }
     }
     GRIDDEP_TRIGGER_LATE();
     if (tile_iter == 0 && warp == 0 && lane == 0) {
@@ -825,9 +924,25 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     args.trace_slot = (args.mode == TC_LOGITS) ? 4 : 2;
     const size_t smem = tc_smem_bytes(nst, bn);
 
-    { int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_kernel, tc_smem_bytes(2, kMaxBN)); if (rc0) return rc0; }
+    { int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_kernel<false>, tc_smem_bytes(2, kMaxBN)); if (rc0) return rc0; }
+    { int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_kernel<true>, tc_smem_bytes(2, kMaxBN)); if (rc0) return rc0; }
+    // Bulk plans (no K split, no deferred reduce; prefill-sized launches and decode steps of thousands of rows)
+    // run PERSISTENT: one CTA per SM, (feature tile, activation tile) items from an atomic counter.  Measured on
+    // the static grid (ncu, profiles/r2_gemm_prefill_ncu.md): the CTAs that own q features have nothing to do on
+    // prefill tiles, so a third of the SMs idled (SM active 65 % of elapsed) unless the grid was many waves deep.
+    args.m_tiles = m_tiles;
+    args.dyn = 0;
+    args.ctr = nullptr;
+    if (split == 1 && !args.defer && (args.mode == TC_STEP || args.mode == TC_PREFILL) && bn == kMaxBN &&
+        !getenv("MLI_TC_STATIC_TILES")) {
+        void* p = nullptr;
+        int rc0 = ws_get_zeroed(ctx, WS_TC_CTR, 64, &p);
+        if (rc0) return rc0;
+        args.ctr = reinterpret_cast<int*>(p) + 2 * (args.mode == TC_STEP ? 0 : 1);
+        args.dyn = 1;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);
+    cfg.gridDim = args.dyn ? dim3((unsigned)ctx->num_sms, 1u, 1u) : dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);
     cfg.blockDim = dim3(kTcThreadsV2);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
@@ -846,7 +961,10 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     }
     cfg.attrs = attrs;
     cfg.numAttrs = (unsigned)na;
-    MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel, w->map_hi, w->map_lo, args));
+    if (args.dyn)
+        MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<true>, w->map_hi, w->map_lo, args));
+    else
+        MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<false>, w->map_hi, w->map_lo, args));
     count_launch();
     return 0;
 }
