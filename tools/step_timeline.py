@@ -24,10 +24,14 @@ WORKLOAD = WORKLOADS["c2a"]
 SLOTS = ["sched_step", "encoder", "QKV+prefill GEMM", "decode attention", "logits GEMM", "decoder"]
 
 
-def measure(device=0, pdl=1):
-    """one traced bench job -> (text report, dict of per-kernel in-graph times)"""
-    wl = WORKLOAD
-    B, S, d, V = wl["B"], wl["S"], wl["d"], wl["V"]
+def measure(device=0, pdl=1, workload="c2a", world=1):
+    """one traced bench job -> (text report, dict of per-kernel in-graph times).  workload / world: the job of
+    rank 0 of `bench.py --workload W` on `world` GPUs (strong workloads shrink with the world size)"""
+    import bench
+    wl = dict(WORKLOADS[workload])
+    S, d, V = wl["S"], wl["d"], wl["V"]
+    strong = wl["n_blocks"] == 0
+    B = wl["B"] // world if strong else wl["B"]
     torch.cuda.set_device(device)
     ctx = mli.Context(device, torch.cuda.current_stream().cuda_stream)
     ctx.set_option(mli.OPT_PDL, pdl)
@@ -36,9 +40,13 @@ def measure(device=0, pdl=1):
     trace[1] = cap
     ctx.call("mli_debug_set_step_trace", trace)
     w = H.make_weights(1001, d, V, S, "Z")
-    offs, toks = H.make_prompts(2002, wl["n_req"], wl["lo"], wl["hi"])
+    offs, toks, _ = bench.rank_requests(wl, 0, world)
+    if strong:
+        plen = np.diff(offs).astype(np.int64)
+        wl["n_blocks"] = int(np.maximum((plen + wl["max_new"] + 1 + 15) // 16, 4).sum()) + 64
+    wl["n_req"] = len(offs) - 1
     dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
-    ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None)
+    ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None, wl["max_new"], 0)
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
     d_offs, d_toks = torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda()
     for _ in range(2):
@@ -65,7 +73,7 @@ def measure(device=0, pdl=1):
     for a, k in enumerate(present):
         nxt = tl[:real - 1, present[a + 1]] if a + 1 < len(present) else tl[1:real, 0]
         dur[:, k] = (nxt - tl[:real - 1, k]) / 1e3
-    lines = [f"# In-graph step timeline, bench workload (B={B}, d={d}, S={S}), pdl={pdl}",
+    lines = [f"# In-graph step timeline, bench workload {workload} on {world} GPU(s): rank 0 (B={B}, d={d}, S={S}), pdl={pdl}",
              "",
              f"{real} engine iterations, {st.generated_tokens} tokens, device job time {st.gpu_ms:.2f} ms "
              f"({1e3 * st.gpu_ms / real:.1f} us / iteration).  Stamp = %globaltimer when the kernel's "
@@ -112,8 +120,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--out", default="")
+    ap.add_argument("--workload", default="c2a")
+    ap.add_argument("--world", type=int, default=1)
     args = ap.parse_args()
-    text, _ = measure(0, args.pdl)
+    text, _ = measure(0, args.pdl, args.workload, args.world)
     print(text)
     if args.out:
         Path(args.out).write_text(text + "\n")
