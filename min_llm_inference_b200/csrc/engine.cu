@@ -159,14 +159,16 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         pq_id = a.queue[(sv.q_head + tid) % sv.q_cap];
         pq_len = a.req_cnt[pq_id];
     }
+    // requests appended by mli_engine_submit / mli_engine_enqueue (the ingest stream publishes the count
+    // after their table rows are complete): ids [sv.n_req, n_avail) are queued in phase 4.  The count is
+    // not produced by the predecessor kernel (any value read is a valid, monotonic snapshot), so it is
+    // fetched with the other early loads
+    const int n_avail = *a.n_avail;
     SCHED_PH(1);
     griddep_wait();
     SCHED_PH(2);
     GRIDDEP_TRIGGER_EARLY();
     trace_stamp(a.trace, 0);
-    // requests appended by mli_engine_submit / mli_engine_enqueue (the ingest stream publishes the count
-    // after their table rows are complete): ids [sv.n_req, n_avail) are queued in phase 4
-    const int n_avail = *a.n_avail;
     if (sv.done && n_avail == sv.n_req) {
         if (tid == 0) {
             a.v->n_new = 0;
@@ -437,9 +439,11 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                 need = max((len + R + kPage - 1) / kPage, MLI_DEFAULT_INIT_NUM_BLOCKS);
                 take = min(need, W);
             }
-            int tott, totl;
+            int tott, totl = 0;
             const int before = take_before + block_scan_excl(take, &tott, s_warp, scan_phase);
-            const int lbefore = len_before + block_scan_excl(len, &totl, s_warp, scan_phase);
+            // (the second scan only when the throttle is on: every block scan is two barriers)
+            const int lbefore = (a.max_prefill > 0)
+                                    ? len_before + block_scan_excl(len, &totl, s_warp, scan_phase) : 0;
             const bool ok = before + need <= F &&
                             (a.max_prefill <= 0 || j == 0 || lbefore + len <= a.max_prefill);
             if (j < n_cand && !ok) atomicMin(&s_carry[1], j);
@@ -551,9 +555,13 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             a.trace[8 + 8 * (a.trace[0] - 1) + 7] = (unsigned long long)n_gran;
         }
         // finished token lists (written by other threads before the barriers above) are complete in
-        // memory before the host can see the new count
-        __threadfence_system();
-        *a.fin_host = a.v->n_fin;
+        // memory before the host can see the new count; only on steps that finished something (a
+        // system-scope fence costs about a microsecond)
+        const int n_fin_now = a.v->n_fin;
+        if (n_fin_now != sv.n_fin || first) {
+            __threadfence_system();
+            *a.fin_host = n_fin_now;
+        }
         // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
         if (n_used + qc == 0) {
             v->done = 1;

@@ -894,6 +894,9 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
                num_kb % (2 * split) == 0)
             split *= 2;
     }
+    // a deferred-reduce launch (logits) that ends up without a K split is a plain bulk GEMM over thousands of
+    // rows: full-width tiles, persistent launch (measured at 8192 rows: 190 us as 512 CTAs of 128 x 128 tiles)
+    if (args.defer && split == 1 && plan_rows >= 4 * kMaxBN) bn = kMaxBN;
     int ny = n_tiles_all;
     const int cap = std::max(1, ctx->num_sms / (m_tiles * split));
     if (ny > cap) ny = std::max(cap, std::min(n_tiles_plan, n_tiles_all));
@@ -933,12 +936,12 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     args.m_tiles = m_tiles;
     args.dyn = 0;
     args.ctr = nullptr;
-    if (split == 1 && !args.defer && (args.mode == TC_STEP || args.mode == TC_PREFILL) && bn == kMaxBN &&
+    if (split == 1 && (args.mode == TC_STEP || args.mode == TC_PREFILL || args.mode == TC_LOGITS) && bn == kMaxBN &&
         !getenv("MLI_TC_STATIC_TILES")) {
         void* p = nullptr;
         int rc0 = ws_get_zeroed(ctx, WS_TC_CTR, 64, &p);
         if (rc0) return rc0;
-        args.ctr = reinterpret_cast<int*>(p) + 2 * (args.mode == TC_STEP ? 0 : 1);
+        args.ctr = reinterpret_cast<int*>(p) + 2 * (args.mode == TC_STEP ? 0 : (args.mode == TC_PREFILL ? 1 : 2));
         args.dyn = 1;
     }
     cudaLaunchConfig_t cfg{};
