@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int F = sv.f_count, fh = sv.f_head, qh = sv.q_head, qc = sv.q_count;
     const int q_cap = sv.q_cap, nb = a.n_blocks;
 
+    int n_fin_now = sv.n_fin;   // finished requests after this step (kept in a register: no read-back)
     if (!first) {
         // ================= phase 1: process_decoder_result (item_storage.cpp:97-139) =================
         int local_gen = 0, local_err = 0;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             n_fin += tot;
         }
         if (tid == 0) a.v->n_fin = n_fin;
+        n_fin_now = n_fin;
 
         SCHED_PH(4);
         // ================= phase 2: free rows in finished_indices (paged_item_storage.cpp:20-32) =====
@@ -557,7 +559,6 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         // finished token lists (written by other threads before the barriers above) are complete in
         // memory before the host can see the new count; only on steps that finished something (a
         // system-scope fence costs about a microsecond)
-        const int n_fin_now = a.v->n_fin;
         if (n_fin_now != sv.n_fin || first) {
             __threadfence_system();
             *a.fin_host = n_fin_now;
