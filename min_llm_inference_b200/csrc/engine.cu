@@ -61,7 +61,6 @@ struct SchedArgs {
     int* counts;      // [0] = number of active rows, [1] = number of granules
     int max_gran;
     volatile int* done_host;  // mapped pinned
-    volatile int* fin_host;   // mapped pinned: number of finished requests (mli_engine_poll_finished)
     volatile int* n_avail;    // device: requests whose table rows are complete (written by the ingest stream);
                               // ids [v->n_req, *n_avail) are waiting to be queued
     unsigned long long* trace;  // optional step timeline
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     int F = sv.f_count, fh = sv.f_head, qh = sv.q_head, qc = sv.q_count;
     const int q_cap = sv.q_cap, nb = a.n_blocks;
 
-    int n_fin_now = sv.n_fin;   // finished requests after this step (kept in a register: no read-back)
+    int n_fin_now = sv.n_fin;   // finished requests after this step
     if (!first) {
         // ================= phase 1: process_decoder_result (item_storage.cpp:97-139) =================
         int local_gen = 0, local_err = 0;
@@ -234,8 +233,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             }
             n_fin += tot;
         }
-        if (tid == 0) a.v->n_fin = n_fin;
-        n_fin_now = n_fin;
+        n_fin_now = n_fin;   // published at the very end of the kernel, after the lists it counts
 
         SCHED_PH(4);
         // ================= phase 2: free rows in finished_indices (paged_item_storage.cpp:20-32) =====
@@ -547,6 +545,12 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         v->admitted = sv.admitted + k_adm;
         v->preemptions = sv.preemptions;
         v->iter = sv.iter + 1;
+        if (n_fin_now != sv.n_fin) {
+            // mli_engine_poll_finished reads this count from another stream while the engine runs: the
+            // token lists and ids it covers (written by other threads, many barriers ago) come first
+            __threadfence();
+            v->n_fin = n_fin_now;
+        }
         v->n_req = n_avail;
         v->max_used = max(sv.max_used, n_used);
         v->min_free = min(sv.min_free, F);
@@ -555,13 +559,6 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         if (a.trace != nullptr && a.trace[0] >= 1 && a.trace[0] - 1 < a.trace[1]) {
             a.trace[8 + 8 * (a.trace[0] - 1) + 6] = (unsigned long long)n_act;    // for tools/step_timeline.py
             a.trace[8 + 8 * (a.trace[0] - 1) + 7] = (unsigned long long)n_gran;
-        }
-        // finished token lists (written by other threads before the barriers above) are complete in
-        // memory before the host can see the new count; only on steps that finished something (a
-        // system-scope fence costs about a microsecond)
-        if (n_fin_now != sv.n_fin || first) {
-            __threadfence_system();
-            *a.fin_host = n_fin_now;
         }
         // is_done (item_storage.cpp:186-188): nothing processing and nothing queued
         if (n_used + qc == 0) {
@@ -607,7 +604,6 @@ __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats
         a.counts[0] = 0;
         a.counts[1] = 0;
         *a.n_avail = 0;
-        *a.fin_host = 0;
     }
 }
 
@@ -690,7 +686,7 @@ struct mli_engine {
     TileDesc* tiles = nullptr;
     int* n_tiles = nullptr;
     int max_tiles = 0;
-    int* done_host = nullptr;  // mapped pinned: [0] done word, [16] finished count
+    int* done_host = nullptr;  // mapped pinned done word
     int* stage_buf = nullptr;  // device staging for host prompts (mli_engine_submit / _enqueue)
     size_t stage_ints = 0;
     std::vector<void*> allocs;
@@ -723,6 +719,7 @@ struct mli_engine {
     // on `io`, both concurrent with the step graphs on `stream`
     cudaStream_t ingest = nullptr, io = nullptr;
     cudaEvent_t reset_ev = nullptr;   // recorded after every reset; the ingest stream waits for it
+    int* cnt_host = nullptr;          // pinned landing word of finished_count()
     int* res_host = nullptr;          // mapped pinned staging for finished lists: ids | offsets | tokens
     int* res_dev = nullptr;           // device alias of res_host
     size_t res_ints = 0;
@@ -930,6 +927,18 @@ int append_requests(mli_engine* e, int first, int n_req, const int* offs, const 
     return 0;
 }
 
+// how many requests have finished so far: a 4-byte copy on the io stream, concurrent with the step graphs
+// (the scheduler publishes the count in device memory only -- a host-visible word would cost it a
+// system-scope fence on every step that retires a request).  A request counted here has its complete token
+// list in the request table: the scheduler instance that wrote both finished before the copy could read.
+int finished_count(mli_engine* e, int* n_fin) {
+    if (!e->cnt_host) MLI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->cnt_host), 64, cudaHostAllocDefault));
+    MLI_CUDA(cudaMemcpyAsync(e->cnt_host, &e->a.v->n_fin, sizeof(int), cudaMemcpyDeviceToHost, e->io));
+    MLI_CUDA(cudaStreamSynchronize(e->io));
+    *n_fin = *e->cnt_host;
+    return 0;
+}
+
 // finished requests [first, first + n) packed into the mapped pinned staging area on the io stream:
 // res_host = ids[n] | offsets[n + 1] | tokens.  Returns after the io stream has drained (the engine's
 // step graphs keep running on their own stream).
@@ -1048,9 +1057,7 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
         int* dptr = nullptr;
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), e->done_host, 0);
         a.done_host = dptr;
-        a.fin_host = dptr + 16;   // its own 64-byte line
         e->done_host[0] = 0;
-        e->done_host[16] = 0;
     }
     cudaEventCreate(&e->ev_submit);
     cudaEventCreate(&e->ev_end);
@@ -1106,6 +1113,7 @@ int mli_engine_destroy(mli_engine* e) {
     if (e->stage_buf) cudaFree(e->stage_buf);
     if (e->done_host) cudaFreeHost(e->done_host);
     if (e->res_host) cudaFreeHost(e->res_host);
+    if (e->cnt_host) cudaFreeHost(e->cnt_host);
     if (e->prof_lengths) cudaFreeHost(e->prof_lengths);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
@@ -1135,7 +1143,6 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
     MLI_CUDA(cudaEventRecord(e->ev_submit, ctx->stream));
     e->submit_timed = true;
     e->done_host[0] = 0;
-    e->done_host[16] = 0;
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(e->a, e->pool, page_floats, e->cfg.max_requests);
     MLI_LAUNCH_CHECK();
     if ((rc = append_requests(e, 0, n_req, prompt_offsets, prompt_tokens, is_device, ctx->stream))) return rc;
@@ -1329,8 +1336,9 @@ int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, 
     MLI_CUDA(cudaStreamSynchronize(e->stream));
     MLI_CUDA(cudaStreamSynchronize(ctx->stream));
     std::lock_guard<std::mutex> lk(e->mu);
-    // everything is final: the count the scheduler last published is exact
-    const int n_fin = *reinterpret_cast<volatile int*>(e->done_host + 16);
+    int n_fin = 0;
+    int rc0 = finished_count(e, &n_fin);
+    if (rc0) return rc0;
     const int *ids, *offs, *toks;
     int rc = gather_finished(e, 0, n_fin, &ids, &offs, &toks);
     if (rc) return rc;
@@ -1347,7 +1355,9 @@ int mli_engine_poll_finished(mli_engine* e, int max_out, int* ids_out, int* offs
     MLI_REQUIRE(e && ids_out && offsets_out && tokens_out && n_out, "null argument");
     MLI_ENTER(e->ctx, "null ctx");
     std::lock_guard<std::mutex> lk(e->mu);
-    const int n_fin = *reinterpret_cast<volatile int*>(e->done_host + 16);
+    int n_fin = 0;
+    int rc0 = finished_count(e, &n_fin);
+    if (rc0) return rc0;
     int n = std::min(std::max(n_fin - e->n_polled, 0), std::max(max_out, 0));
     *n_out = 0;
     offsets_out[0] = 0;

@@ -698,6 +698,384 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bulk plan on CTA PAIRS (tcgen05 cta_group::2).  Same work items as the persistent launch above, but
+// an item is (activation tile of 256 rows, PAIR of feature tiles): the two CTAs of a cluster sit on
+// the two SMs of a TPC and issue ONE 256 x 256 x 8 MMA per k-step (the leader's thread issues it for
+// both).  Each CTA keeps its own 128 features of the weight tile (A operand, by TMA) and converts only
+// HALF of the activation rows (B operand: rows [rank * n/2, (rank + 1) * n/2) of the tile); the tensor
+// cores read the other half from the peer's shared memory.  Per 32-wide k-block a CTA therefore moves
+// 96 KB of MMA operands + 32 KB of converter stores + 32 KB of TMA writes through its shared memory
+// instead of 144 + 64 + 32 KB, which takes the main loop from shared-memory-bound (1900 cycles per
+// k-block, measured 1800) to MMA-bound (1570), and halves the gather / split work per CTA.
+//   full_w / full_x of the LEADER collect both CTAs (the peer's TMA completes its bytes on the
+//   leader's barrier: cp.async.bulk.tensor.cta_group::2; the peer's converter warps arrive remotely);
+//   empty / accumulator-complete barriers are signalled in both CTAs by multicast commits.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPairStages = 3;
+constexpr int kPairHalf = kMaxBN / 2;                           // activation rows a CTA converts
+constexpr int kPairXBytes = kPairHalf * kBK * 4;                // 16 KB (each of hi, lo)
+constexpr int kPairStageBytes = 2 * kWBytes + 2 * kPairXBytes;  // 64 KB
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// executed by both CTAs of the pair; the bytes complete on the LEADER's barrier (peer bit of the shared
+// window address cleared, as cute::SM100_TMA_2SM_LOAD does)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
+    const uint32_t ra = dsmem_addr(bar, cta_rank);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void st_dsmem_i32(uint32_t addr, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// items in units of feature-tile PAIRS
+__device__ __forceinline__ TcItems tc_items_pair(const TcArgs& args, int n_valid) {
+    TcItems t;
+    const int n_tiles = (n_valid + kMaxBN - 1) / kMaxBN;
+    const int m_units = args.m_tiles / 2;
+    if (args.mode == TC_STEP) {
+        const int pad = (args.counts[0] + 15) & ~15;
+        t.a_tiles = min(n_tiles, (pad + kMaxBN - 1) / kMaxBN);
+        t.kv_tiles = args.d / kBM;          // 2 matrices x (d / 128) / 2 pairs
+    } else {
+        t.a_tiles = n_tiles;
+        t.kv_tiles = m_units;
+    }
+    t.n_items = t.a_tiles * m_units + (n_tiles - t.a_tiles) * t.kv_tiles;
+    return t;
+}
+__device__ __forceinline__ void tc_item_pair(const TcArgs& args, const TcItems& t, int item, int* mu, int* nt) {
+    const int m_units = args.m_tiles / 2;
+    const int full = t.a_tiles * m_units;
+    if (item < full) {
+        *nt = item / m_units;
+        *mu = item % m_units;
+    } else {
+        const int u = item - full;
+        *nt = t.a_tiles + u / t.kv_tiles;
+        const int k = u % t.kv_tiles, per = args.d / (2 * kBM);
+        *mu = (k < per) ? k : k + per;   // K pairs, then V pairs (the q block is skipped)
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreadsV2, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                        TcArgs args) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TC_STAMP(0);
+    constexpr int nst = kPairStages;
+    constexpr int stage_bytes = kPairStageBytes;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_pairs = (int)gridDim.x >> 1;
+
+    unsigned char* base = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* ctrl = base + (size_t)nst * stage_bytes;
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(ctrl);
+    uint64_t* full_x = full_w + kMaxTcStages;
+    uint64_t* empty_bar = full_x + kMaxTcStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxTcStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    int* s_next_item = reinterpret_cast<int*>(tmem_ptr_smem + 2);   // [2], same offset in both CTAs
+    const float** src_tab = reinterpret_cast<const float**>(ctrl + 256);
+    float** dst_tab = reinterpret_cast<float**>(ctrl + 256 + kMaxBN * 8);
+    float* part = reinterpret_cast<float*>(base);   // [256][128] tile of this CTA's features, aliases the stages
+    __shared__ TcItems s_items;
+
+    int m0 = 0, mat = 0, f0 = 0;
+    auto set_features = [&](int m_tile) {
+        m0 = m_tile * kBM;
+        mat = 0;
+        f0 = m0;
+        if (args.mode != TC_LOGITS) {
+            mat = m0 / args.d;
+            f0 = m0 % args.d;
+            if (args.mode == TC_PREFILL && mat == 1) mat = 2;
+        }
+    };
+    // first item of the pair = its index (counts are final before this kernel can start, see gemm_tf32x3_kernel)
+    int item = (int)blockIdx.x >> 1, nt = 0, n_items = 0;
+    {
+        const TcItems items = tc_items_pair(args, tc_n_valid(args));
+        if (tid == 0) s_items = items;
+        n_items = items.n_items;
+        if (item < n_items) {
+            int mu;
+            tc_item_pair(args, items, item, &mu, &nt);
+            set_features(2 * mu + (int)rank);
+        }
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi);
+        prefetch_tmap(&map_a_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full_w[s], 1);                               // the leader's expect_tx arrival
+            mbar_init(&full_x[s], 2 * (kTcConvThreads / 32));       // converter warps of both CTAs
+            mbar_init(&empty_bar[s], 1);                            // multicast commit
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(tmem_ptr_smem, (uint32_t)args.tmem_cols);
+    tc_fence_before();
+    cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_ptr_smem;
+
+    TC_STAMP(1);
+    const int num_kb = args.K / kBK;
+    const int kb_per_acc = (num_kb + args.n_acc - 1) / args.n_acc;
+    const int n_pre = (item >= n_items) ? 0 : min(nst, num_kb);
+    const uint64_t w_policy = l2_policy_evict_last();
+    auto load_weights = [&](int s, int kb) {
+        unsigned char* st = base + (size_t)s * stage_bytes;
+        if (leader) mbar_expect_tx(&full_w[s], 4 * kWBytes);   // hi + lo of both CTAs
+        tma_load_2d_2sm(st, &map_a_hi, kb * kBK, m0, &full_w[s], w_policy);
+        tma_load_2d_2sm(st + kWBytes, &map_a_lo, kb * kBK, m0, &full_w[s], w_policy);
+    };
+    if (warp == 0 && lane == 0)
+        for (int i = 0; i < n_pre; ++i) load_weights(i, i);
+    griddep_wait();
+    GRIDDEP_TRIGGER_EARLY();
+    trace_stamp(args.trace, args.trace_slot);
+
+    const int n_valid = tc_n_valid(args);
+    uint32_t it = 0, tile_iter = 0;
+    while (item < n_items) {
+        // the leader claims the pair's NEXT item and leaves it in both CTAs; it is read after the cluster
+        // barrier that ends this tile
+        if (leader && tid == 0) {
+            const int nxt = n_pairs + atomicAdd(&args.ctr[0], 1);
+            s_next_item[tile_iter & 1] = nxt;
+            st_dsmem_i32(dsmem_addr(&s_next_item[tile_iter & 1], 1), nxt);
+        }
+        const int n0 = nt * kMaxBN;
+        const int n_eff = min(kMaxBN, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
+        const int n_half = n_eff >> 1;                                // rows this CTA converts
+        if (tid < kMaxBN) {
+            const RowIO io = row_io(args, n0 + tid, n_valid, mat, f0);
+            src_tab[tid] = io.src;
+            dst_tab[tid] = io.dst;
+        }
+        __syncthreads();
+
+        if (warp == 0) {
+            // ===================== TMA producer (this CTA's weight tile) =====================
+            if (lane == 0) {
+                uint32_t i = it;
+                for (int kb = 0; kb < num_kb; ++kb, ++i) {
+                    if (tile_iter == 0 && kb < n_pre) continue;   // issued before the wait
+                    const int s = i % nst;
+                    mbar_wait(&empty_bar[s], ((i / nst) & 1) ^ 1);
+                    load_weights(s, kb);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            if (leader && lane == 0) {
+                const uint32_t idesc = make_idesc_tf32(2 * kBM, n_eff);
+                uint32_t i = it;
+                for (int kb = 0; kb < num_kb; ++kb, ++i) {
+                    const int s = i % nst;
+                    const uint32_t ph = (i / nst) & 1;
+                    mbar_wait(&full_w[s], ph);
+                    mbar_wait(&full_x[s], ph);
+                    tc_fence_after();
+                    unsigned char* st = base + (size_t)s * stage_bytes;
+                    const uint64_t a_hi = make_kmajor_sw128_desc(st);
+                    const uint64_t a_lo = make_kmajor_sw128_desc(st + kWBytes);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kWBytes);
+                    const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * kWBytes + kPairXBytes);
+                    const uint32_t acc = tmem_acc + (uint32_t)((kb / kb_per_acc) * args.acc_stride);
+                    const bool first_kb = (kb % kb_per_acc) == 0;
+                    if (kb == 0) TC_STAMP(2);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint64_t koff = (uint64_t)((k * kUmmaK * 4) >> 4);
+                        umma_tf32_2sm(acc, a_lo + koff, b_hi + koff, idesc, (first_kb && k == 0) ? 0u : 1u);
+                        umma_tf32_2sm(acc, a_hi + koff, b_lo + koff, idesc, 1);
+                        umma_tf32_2sm(acc, a_hi + koff, b_hi + koff, idesc, 1);
+                    }
+                    umma_commit_pair(&empty_bar[s]);
+                }
+                umma_commit_pair(tmem_full_bar);
+            }
+            __syncwarp();
+        } else if (warp >= 4) {
+            // ===================== activation gather + tf32 split (this CTA's half of the rows) =====================
+            const int c = tid - 128;
+            const int chunk = c & 7;
+            const int rbase = c >> 3;
+            const float4* rp[kPairHalf / 32];
+#pragma unroll
+            for (int i = 0; i < kPairHalf / 32; ++i) {
+                const int r = rbase + 32 * i;
+                const float* p = (r < n_half) ? src_tab[(int)rank * n_half + r] : nullptr;
+                rp[i] = p ? reinterpret_cast<const float4*>(p) + chunk : nullptr;
+            }
+            float4 ra[kPairHalf / 32], rb[kPairHalf / 32];
+            auto load_set = [&](float4 (&dst)[kPairHalf / 32], int kb) {
+#pragma unroll
+                for (int i = 0; i < kPairHalf / 32; ++i)
+                    dst[i] = rp[i] ? ldg_stream(rp[i] + kb * (kBK / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            auto store_set = [&](const float4 (&src)[kPairHalf / 32], uint32_t i2) {
+                const int s = i2 % nst;
+                mbar_wait(&empty_bar[s], ((i2 / nst) & 1) ^ 1);
+                unsigned char* xh = base + (size_t)s * stage_bytes + 2 * kWBytes;
+                unsigned char* xl = xh + kPairXBytes;
+#pragma unroll
+                for (int i = 0; i < kPairHalf / 32; ++i) {
+                    const int r = rbase + 32 * i;
+                    if (r < n_half) {
+                        const float4 v = src[i];
+                        const float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z),
+                                                     to_tf32_rna(v.w));
+                        const float4 l = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y),
+                                                     to_tf32_rna(v.z - h.z), to_tf32_rna(v.w - h.w));
+                        const int off = r * 128 + ((chunk ^ (r & 7)) << 4);   // 128B swizzle
+                        *reinterpret_cast<float4*>(xh + off) = h;
+                        *reinterpret_cast<float4*>(xl + off) = l;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive(&full_x[s]);
+                    else mbar_arrive_remote(&full_x[s], 0);
+                }
+            };
+            load_set(ra, 0);
+            if (1 < num_kb) load_set(rb, 1);
+            uint32_t i2 = it;
+            for (int kb = 0; kb < num_kb; kb += 2, i2 += 2) {
+                store_set(ra, i2);
+                if (kb + 2 < num_kb) load_set(ra, kb + 2);
+                if (kb + 1 < num_kb) {
+                    store_set(rb, i2 + 1);
+                    if (kb + 3 < num_kb) load_set(rb, kb + 3);
+                }
+            }
+            TC_STAMP(3);
+            // ===================== epilogue: this CTA's 128 features x all rows of the tile =====================
+            mbar_wait(tmem_full_bar, tile_iter & 1);
+            tc_fence_after();
+            TC_STAMP(4);
+            const int q = warp & 3;
+            const int half = (warp - 4) >> 2;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            for (int c0 = half * 32; c0 < n_eff; c0 += 64) {
+                float v[32];
+                tmem_ld32(tmem_acc + lane_base + (uint32_t)c0, v);
+                for (int a = 1; a < args.n_acc; ++a) {
+                    float u[32];
+                    tmem_ld32(tmem_acc + lane_base + (uint32_t)(a * args.acc_stride + c0), u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += u[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < n_eff) part[(size_t)(c0 + j) * kBM + q * 32 + lane] = v[j];
+            }
+            tc_fence_before();
+        }
+        cluster_sync_all();   // both CTAs' MMAs have read every stage; both accumulators are in `part`
+        TC_STAMP(5);
+        {
+            const size_t plane = 0;
+            const int f4 = tid & 31;
+            const bool to_bf16 = args.kv_bf16 && args.mode != TC_LOGITS && mat != 1;
+            for (int n = tid >> 5; n < n_eff; n += kTcThreadsV2 / 32) {
+                float* p = dst_tab[n];
+                if (p == nullptr) continue;
+                const float4 v = *reinterpret_cast<const float4*>(part + (size_t)n * kBM + f4 * 4);
+                if (to_bf16) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    reinterpret_cast<uint2*>(p + plane)[f4] = u;
+                } else {
+                    reinterpret_cast<float4*>(p + plane)[f4] = v;
+                }
+            }
+        }
+        TC_STAMP(6);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        cluster_sync_all();   // `part` and the row tables may be reused; the next item id has landed
+        tc_fence_after();
+        it += (uint32_t)num_kb;
+        ++tile_iter;
+        item = s_next_item[(tile_iter - 1) & 1];
+        if (item < n_items) {
+            int mu;
+            tc_item_pair(args, s_items, item, &mu, &nt);
+            set_features(2 * mu + (int)rank);
+        }
+    }
+    if (leader && tid == 0) {
+        __threadfence();
+        if (atomicAdd(&args.ctr[1], 1) == n_pairs - 1) {   // last pair out re-arms the counters
+            args.ctr[0] = 0;
+            args.ctr[1] = 0;
+            __threadfence();
+        }
+    }
+    GRIDDEP_TRIGGER_LATE();
+    tc_fence_before();
+    cluster_sync_all();   // neither CTA leaves while the other may still signal it
+    TC_STAMP(7);
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_acc, (uint32_t)args.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------
 // Wt_hi/lo[(mat*d + f)][k] = split(W_mat[k][f]) : transpose to K-major + tf32 split (one time)
@@ -944,15 +1322,23 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
         args.ctr = reinterpret_cast<int*>(p) + 2 * (args.mode == TC_STEP ? 0 : (args.mode == TC_PREFILL ? 1 : 2));
         args.dyn = 1;
     }
+    // ... and on CTA pairs (cta_group::2) when the feature tiles pair up: emb_dim a multiple of 256
+    const bool pair = args.dyn && m_tiles % 2 == 0 && (args.mode == TC_LOGITS || (args.d / kBM) % 2 == 0) &&
+                      args.n_acc * args.acc_stride <= 512 && !getenv("MLI_TC_NO_PAIR");
+    if (pair) {
+        int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_pair_kernel, tc_smem_bytes(kPairStages, kPairHalf));
+        if (rc0) return rc0;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = args.dyn ? dim3((unsigned)ctx->num_sms, 1u, 1u) : dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);
+    cfg.gridDim = args.dyn ? dim3((unsigned)(pair ? (ctx->num_sms & ~1) : ctx->num_sms), 1u, 1u)
+                           : dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);
     cfg.blockDim = dim3(kTcThreadsV2);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attrs[2];
     int na = 0;
     attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = 1;
+    attrs[na].val.clusterDim.x = pair ? 2 : 1;
     attrs[na].val.clusterDim.y = 1;
     attrs[na].val.clusterDim.z = args.defer ? 1u : (unsigned)split;   // deferred: ranks are independent
     ++na;
@@ -964,7 +1350,10 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     }
     cfg.attrs = attrs;
     cfg.numAttrs = (unsigned)na;
-    if (args.dyn)
+    if (pair) {
+        cfg.dynamicSmemBytes = tc_smem_bytes(kPairStages, kPairHalf);
+        MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel, w->map_hi, w->map_lo, args));
+    } else if (args.dyn)
         MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<true>, w->map_hi, w->map_lo, args));
     else
         MLI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<false>, w->map_hi, w->map_lo, args));
