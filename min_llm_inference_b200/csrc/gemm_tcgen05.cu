@@ -141,6 +141,18 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// the same rounding (to nearest, ties away from zero, low 13 mantissa bits cleared) with two full-rate integer
+// instructions: cvt.rna.tf32.f32 was measured to dominate the activation converters (32 conversions per thread and
+// k-block: ~1000 cycles per k-block for a warp, tools/ncu_jobs.py prefill_stamps).  Bit-identical for finite values.
+__device__ __forceinline__ float to_tf32_rna_int(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
+    h = make_float4(to_tf32_rna_int(v.x), to_tf32_rna_int(v.y), to_tf32_rna_int(v.z), to_tf32_rna_int(v.w));
+    l = make_float4(to_tf32_rna_int(v.x - h.x), to_tf32_rna_int(v.y - h.y), to_tf32_rna_int(v.z - h.z),
+                    to_tf32_rna_int(v.w - h.w));
+}
+
 enum TcMode { TC_LATEST = 0, TC_PREFILL = 1, TC_LOGITS = 2, TC_STEP = 3 };
 
 struct TcArgs {
@@ -553,6 +565,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 for (int i = 0; i < kMaxBN / 32; ++i) {
                     const int r = rbase + 32 * i;
                     if (r < n_eff) {
+                        // (cvt.rna here: the integer rounding of the pair kernel costs this one, which holds eight
+                        // rows per thread, its last registers -- 88 bytes of spills)
                         const float4 v = src[i];
                         const float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z),
                                                      to_tf32_rna(v.w));
@@ -853,7 +867,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < nst; ++s) {
             mbar_init(&full_w[s], 1);                               // the leader's expect_tx arrival
-            mbar_init(&full_x[s], 2 * (kTcConvThreads / 32));       // converter warps of both CTAs
+            mbar_init(&full_x[s], 2 * (kTcConvThreads / 64));       // one group of four converter warps in each CTA
             mbar_init(&empty_bar[s], 1);                            // multicast commit
         }
         mbar_init(tmem_full_bar, 1);
@@ -919,11 +933,24 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             if (leader && lane == 0) {
                 const uint32_t idesc = make_idesc_tf32(2 * kBM, n_eff);
                 uint32_t i = it;
+                // diagnostics (tools/ncu_jobs.py prefill_stamps): cycles this item's issuer spent waiting for
+                // weights / for activations, in row 2048 + cta of the stamp buffer
+                long long w_wait = 0, x_wait = 0;
+                const long long t_item = args.dbg ? clock64() : 0;
                 for (int kb = 0; kb < num_kb; ++kb, ++i) {
                     const int s = i % nst;
                     const uint32_t ph = (i / nst) & 1;
-                    mbar_wait(&full_w[s], ph);
-                    mbar_wait(&full_x[s], ph);
+                    if (args.dbg) {
+                        const long long t0 = clock64();
+                        mbar_wait(&full_w[s], ph);
+                        const long long t1 = clock64();
+                        mbar_wait(&full_x[s], ph);
+                        w_wait += t1 - t0;
+                        x_wait += clock64() - t1;
+                    } else {
+                        mbar_wait(&full_w[s], ph);
+                        mbar_wait(&full_x[s], ph);
+                    }
                     tc_fence_after();
                     unsigned char* st = base + (size_t)s * stage_bytes;
                     const uint64_t a_hi = make_kmajor_sw128_desc(st);
@@ -943,64 +970,87 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     umma_commit_pair(&empty_bar[s]);
                 }
                 umma_commit_pair(tmem_full_bar);
+                if (args.dbg) {
+                    long long* row = args.dbg + (size_t)(2048 + blockIdx.x) * 8;
+                    row[0] = w_wait;
+                    row[1] = x_wait;
+                    row[2] = clock64() - t_item;   // issue loop of the item, waits included
+                    row[3] = num_kb;
+                    row[4] += 1;                   // items this pair has processed
+                }
             }
             __syncwarp();
         } else if (warp >= 4) {
             // ===================== activation gather + tf32 split (this CTA's half of the rows) =====================
-            const int c = tid - 128;
-            const int chunk = c & 7;
-            const int rbase = c >> 3;
-            const float4* rp[kPairHalf / 32];
+            // Two groups of four warps take the even / the odd k-blocks.  Measured with the earlier scheme (all
+            // eight warps on every k-block, raw rows prefetched into registers two or four k-blocks ahead;
+            // tools/ncu_jobs.py prefill_stamps): the proxy fence that publishes a stage to the tensor core also
+            // waits for the thread's OUTSTANDING GLOBAL LOADS, so every k-block paid a memory round trip (700-1400
+            // cycles in the fence) and the MMA issuer waited for activations 46 % of an item.  Here a thread has
+            // nothing in flight when it fences (it loads, converts, stores, fences, then loads again), and a
+            // group has two MMA periods (~3100 cycles) for that round trip.
+            const int grp = (warp - 4) >> 2;          // 0: even k-blocks, 1: odd
+            const int c = tid - 128 - grp * 128;      // 0..127 inside the group
+            const int chunk = c & 7;                  // 16-byte chunk of the 128-byte k-slice
+            const int rbase = c >> 3;                 // rows rbase, rbase + 16, ...
+            constexpr int kRows = kPairHalf / 16;     // 8 rows per thread
+            const float4* rp[kRows];
 #pragma unroll
-            for (int i = 0; i < kPairHalf / 32; ++i) {
-                const int r = rbase + 32 * i;
+            for (int i = 0; i < kRows; ++i) {
+                const int r = rbase + 16 * i;
                 const float* p = (r < n_half) ? src_tab[(int)rank * n_half + r] : nullptr;
                 rp[i] = p ? reinterpret_cast<const float4*>(p) + chunk : nullptr;
             }
-            float4 ra[kPairHalf / 32], rb[kPairHalf / 32];
-            auto load_set = [&](float4 (&dst)[kPairHalf / 32], int kb) {
+            long long c_wait = 0, c_store = 0, c_fence = 0, c_arrive = 0;   // diagnostics: warp 4's time per phase of an item
+            const bool c_dbg = args.dbg != nullptr && warp == 4;
+            uint32_t i2 = it + (uint32_t)grp;
+            for (int kb = grp; kb < num_kb; kb += 2, i2 += 2) {
+                float4 raw[kRows];
 #pragma unroll
-                for (int i = 0; i < kPairHalf / 32; ++i)
-                    dst[i] = rp[i] ? ldg_stream(rp[i] + kb * (kBK / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            auto store_set = [&](const float4 (&src)[kPairHalf / 32], uint32_t i2) {
+                for (int i = 0; i < kRows; ++i)
+                    raw[i] = rp[i] ? ldg_stream(rp[i] + kb * (kBK / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const int s = i2 % nst;
-                mbar_wait(&empty_bar[s], ((i2 / nst) & 1) ^ 1);
+                const long long t0 = c_dbg ? clock64() : 0;
+                if (lane == 0) mbar_wait(&empty_bar[s], ((i2 / nst) & 1) ^ 1);   // one poller per warp
+                __syncwarp();
+                const long long t1 = c_dbg ? clock64() : 0;
                 unsigned char* xh = base + (size_t)s * stage_bytes + 2 * kWBytes;
                 unsigned char* xl = xh + kPairXBytes;
 #pragma unroll
-                for (int i = 0; i < kPairHalf / 32; ++i) {
-                    const int r = rbase + 32 * i;
+                for (int i = 0; i < kRows; ++i) {
+                    const int r = rbase + 16 * i;
                     if (r < n_half) {
-                        const float4 v = src[i];
-                        const float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z),
-                                                     to_tf32_rna(v.w));
-                        const float4 l = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y),
-                                                     to_tf32_rna(v.z - h.z), to_tf32_rna(v.w - h.w));
+                        float4 h, l;
+                        split_tf32(raw[i], h, l);
                         const int off = r * 128 + ((chunk ^ (r & 7)) << 4);   // 128B swizzle
                         *reinterpret_cast<float4*>(xh + off) = h;
                         *reinterpret_cast<float4*>(xl + off) = l;
                     }
                 }
+                const long long t2 = c_dbg ? clock64() : 0;
                 fence_proxy_async_smem();
+                const long long t2b = c_dbg ? clock64() : 0;
                 __syncwarp();
                 if (lane == 0) {
                     if (leader) mbar_arrive(&full_x[s]);
                     else mbar_arrive_remote(&full_x[s], 0);
                 }
-            };
-            load_set(ra, 0);
-            if (1 < num_kb) load_set(rb, 1);
-            uint32_t i2 = it;
-            for (int kb = 0; kb < num_kb; kb += 2, i2 += 2) {
-                store_set(ra, i2);
-                if (kb + 2 < num_kb) load_set(ra, kb + 2);
-                if (kb + 1 < num_kb) {
-                    store_set(rb, i2 + 1);
-                    if (kb + 3 < num_kb) load_set(rb, kb + 3);
+                if (c_dbg) {
+                    const long long t3 = clock64();
+                    c_wait += t1 - t0;
+                    c_store += t2 - t1;
+                    c_fence += t2b - t2;
+                    c_arrive += t3 - t2b;
                 }
             }
             TC_STAMP(3);
+            if (c_dbg && lane == 0) {
+                long long* row = args.dbg + (size_t)(2304 + blockIdx.x) * 8;
+                row[0] = c_wait;
+                row[1] = c_store;
+                row[2] = c_fence;
+                row[3] = c_arrive;
+            }
             // ===================== epilogue: this CTA's 128 features x all rows of the tile =====================
             mbar_wait(tmem_full_bar, tile_iter & 1);
             tc_fence_after();

@@ -49,7 +49,7 @@ def attn_job(key):
     ctx.close()
 
 
-def prefill():
+def prefill(stamps=False):
     """one engine step at B = 1024 rows (the launch plan of the large configurations: no split-K, 32 tile
     walkers per feature tile) that admits 256 prompts of ~1900 tokens and 768 short ones: ~0.5 M positions"""
     torch.cuda.set_device(0)
@@ -66,11 +66,48 @@ def prefill():
     ec = mli.EngineCfg(B, S, d, V, n_blocks, 1, 0, n_req, None, 4, 0)
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
     ms = []
+    if stamps:   # before the step graph is captured (the pointer is baked into the kernel arguments)
+        buf = torch.zeros((4096, 8), dtype=torch.int64, device="cuda")
+        ctx.call("mli_debug_set_gemm_stamps", buf)
     for rep in range(2):
         eng.submit(torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda(), is_device=True)
         eng.run(max_steps=1)
         ms.append(eng.stats().gpu_ms)
     pos = int(offs[-1])
+    if stamps:
+        # clock64 phase stamps of the LAST item every CTA processed (slots: 0 start, 1 set-up done, 2 first MMA of the
+        # item issued, 3 converters done, 4 accumulators complete, 5 after the exchange barrier, 6 rows stored, 7 end)
+        torch.cuda.synchronize()
+        buf.zero_()
+        eng.submit(torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda(), is_device=True)
+        eng.run(max_steps=1)
+        torch.cuda.synchronize()
+        st = buf.cpu().numpy()
+        nz = st[st[:, 0] != 0]
+        print(f"{len(nz)} stamped CTAs; kernel cycles (t7 - t0): {np.sort((nz[:, 7] - nz[:, 0]))[::max(1, len(nz) // 12)].tolist()}")
+        print("sample rows (deltas):", np.diff(nz[-4:], axis=1).tolist())
+        mm = buf.cpu().numpy()[2048:2048 + 160]
+        mm = mm[mm[:, 3] != 0]
+        if len(mm):
+            print(f"MMA issuer of {len(mm)} pairs, last item: wait for weights {mm[:, 0].mean():.0f}, wait for activations "
+                  f"{mm[:, 1].mean():.0f}, whole issue loop {mm[:, 2].mean():.0f} cycles over {mm[0, 3]} k-blocks; items per pair "
+                  f"{mm[:, 4].mean():.1f}")
+        cv = buf.cpu().numpy()[2304:2304 + 160]
+        for nm, sel in (("leader CTAs", cv[0::2]), ("peer CTAs", cv[1::2])):
+            sel = sel[sel[:, 1] != 0]
+            if len(sel):
+                print(f"converter warp 4 of {len(sel)} {nm}, last item (its 16 k-blocks): waiting for a free stage {sel[:, 0].mean():.0f}, "
+                      f"convert + store (incl. waiting for the loads) {sel[:, 1].mean():.0f}, proxy fence {sel[:, 2].mean():.0f}, "
+                      f"syncwarp + arrive {sel[:, 3].mean():.0f} cycles")
+        st = nz[(nz[:, 7] - nz[:, 0]) > 1000000]
+        if not len(st):
+            return
+        names = ["main loop of the last item (first MMA -> converters done)", "MMA tail (converters done -> accumulators complete)",
+                 "TMEM -> smem + barrier", "rows to global"]
+        print(f"{len(st)} CTAs with a long run; kernel {np.mean(st[:, 7] - st[:, 0]):.0f} cycles")
+        for i, nm in zip((2, 3, 4, 5), names):
+            col = (st[:, i + 1] - st[:, i]).astype(np.float64)
+            print(f"  {nm:60s} mean {col.mean():8.0f}  min {col.min():8.0f}  max {col.max():8.0f} cycles")
     print(json.dumps({"prefill_positions": pos, "fp32_equivalent_flops": 4.0 * (pos - n_req) * d * d + 6.0 * B * d * d,
                       "rows": B, "emb_dim": d, "kv_pool_gb": n_blocks * 16 * 3 * d * 4 / 1e9, "step_ms": ms}), flush=True)
     eng.close()
@@ -114,5 +151,7 @@ if __name__ == "__main__":
         attn_job(sys.argv[2] if len(sys.argv) > 2 else "c4")
     elif what == "prefill":
         prefill()
+    elif what == "prefill_stamps":
+        prefill(stamps=True)
     else:
         attn_one()
