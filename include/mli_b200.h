@@ -287,7 +287,10 @@ int mli_engine_results(mli_engine* e, int* finished_ids, int* finished_offsets, 
  * ItemStorage::pop_finished_items, src/item_storage.cpp:97-139): the requests that finished since the
  * last poll, in finish order, HOST buffers: ids[max_out], offsets[max_out+1], tokens[tokens_capacity]
  * (prompt + generated, packed).  Never waits for the engine: the finished count is read and the token
- * lists are packed into mapped pinned memory on a side stream while the step graphs keep running.  Callable from another host thread during mli_engine_run.  *n_out may be 0. */
+ * lists are packed into mapped pinned memory on a side stream while the step graphs keep running.  Callable from another host thread during mli_engine_run.  *n_out may be 0; it always is on
+ * the first call after a submit, which only tells the device scheduler that polling is in use (from then on
+ * it orders a step's finished lists before the count it publishes; a job that never polls does not pay for
+ * that fence). */
 int mli_engine_poll_finished(mli_engine* e, int max_out, int* ids, int* offsets, int* tokens,
                              long long tokens_capacity, int* n_out);
 /* device-to-device copy of the request table (tokens[n_req][n_sequence], counts[n_req]) into
