@@ -93,7 +93,10 @@ def main():
             ctx.set_option(mli.OPT_KV_FORMAT, 1)
         if os.environ.get("ATTN_KERNEL"):
             ctx.set_option(mli.OPT_ATTN_KERNEL, int(os.environ["ATTN_KERNEL"]))   # 1 column-split, 2 warp-per-position
+        only = os.environ.get("ATTN_ONLY", "")
         for sh in SHAPES:
+            if only and only not in sh[0]:
+                continue
             r = one(ctx, *sh, kv_bf16)
             r["frac_of_measured_peak"] = r["GBps"] / peak
             rows.append(r)
