@@ -65,7 +65,7 @@ def workload_config(wl, world):
             "n_sequence": wl["S"], "n_vocab": wl["V"], "requests_total": wl["n_req"] if strong else wl["n_req"] * world,
             "prompt_lengths": f"U[{wl['lo']},{wl['hi']}]", "max_new_tokens": wl["max_new"], "n_forward_rounds": wl["R"],
             "distribution": "Z (zero-mean), fixed seeds", "lengths": "corrected (no Q1 replay)",
-            "parallelism": f"request-sharded dp{world}",
+            "parallelism": f"request-sharded dp{world}" + (" (prompt-length-balanced shards)" if strong else ""),
             "step": "one whole job (every request of the rank admitted, prefilled, decoded, retired; token gather)"}
 
 
@@ -143,11 +143,13 @@ class StdoutToStderr:
 def rank_requests(wl, rank, world):
     """(local offsets, local tokens) of this rank: strong scaling shards ONE global request set"""
     import harness as H
-    from min_llm_inference_b200.sharding import shard_requests
+    from min_llm_inference_b200.sharding import shard_requests, shard_requests_balanced
     strong = wl["n_blocks"] == 0
     n_total = wl["n_req"] if strong else wl["n_req"] * world
     g_offs, g_toks = H.make_prompts(SEED_P, n_total, wl["lo"], wl["hi"])
-    offs, toks, _ = shard_requests(g_offs, g_toks, rank, world)
+    # strong scaling: the router balances prompt tokens between the ranks (the job time is the max over ranks)
+    split = shard_requests_balanced if strong else shard_requests
+    offs, toks, _ = split(g_offs, g_toks, rank, world)
     return offs, toks, n_total
 
 

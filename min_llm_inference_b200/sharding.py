@@ -17,6 +17,26 @@ def shard_requests(offsets: np.ndarray, tokens: np.ndarray, rank: int, world: in
     return local_offs, local_toks, np.arange(lo, hi, dtype=np.int64)
 
 
+def shard_requests_balanced(offsets: np.ndarray, tokens: np.ndarray, rank: int, world: int):
+    """prompt-length-balanced sharding: requests sorted by length and dealt to the ranks in a snake
+    (0..G-1, G-1..0, ...), so every rank gets the same number of requests (+-1) and the same number of
+    prompt tokens to within a fraction of a percent -- the attention bytes of a decode step follow the
+    context lengths, and the job time is the MAX over ranks.  Contiguous blocks of the synthetic set differ
+    by 1.4 % at 8 ranks.  Returns (local offsets, local tokens, global ids of the local requests)."""
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    order = np.argsort(-lens, kind="stable")
+    pos = np.arange(n)
+    lane = np.where((pos // world) % 2 == 0, pos % world, world - 1 - pos % world)
+    ids = np.sort(order[lane == rank]).astype(np.int64)
+    local_lens = lens[ids]
+    local_offs = np.zeros(len(ids) + 1, np.int32)
+    local_offs[1:] = np.cumsum(local_lens)
+    local_toks = np.concatenate([tokens[offsets[i]:offsets[i + 1]] for i in ids]).astype(np.int32) if len(ids) else \
+        np.zeros(0, np.int32)
+    return local_offs, local_toks, ids
+
+
 def gather_tokens(local_tokens, local_counts, n_total: int):
     """all-gather the per-rank request tables [n_local, S] (+ counts) into [n_total, S] on every rank.
     local_* are torch tensors on the backend's device; ranks may hold unequal request counts."""

@@ -67,3 +67,21 @@ def test_shard_requests_partition():
                 assert np.array_equal(lt[lo[k]:lo[k + 1]], toks[offs[g]:offs[g + 1]])
             seen.extend(ids.tolist())
         assert sorted(seen) == list(range(10))
+
+
+def test_balanced_sharding_is_a_partition():
+    """shard_requests_balanced: every request lands on exactly one rank, the ranks' prompt-token totals agree to
+    within a percent, and the local (offsets, tokens) reproduce the global prompts"""
+    from min_llm_inference_b200.sharding import shard_requests_balanced
+    offs, toks = H.make_prompts(7, 1001, 4, 500)
+    for world in (1, 2, 3, 8):
+        seen, totals = [], []
+        for rank in range(world):
+            lo, lt, ids = shard_requests_balanced(offs, toks, rank, world)
+            assert len(lo) - 1 == len(ids)
+            for k, g in enumerate(ids):
+                assert np.array_equal(lt[lo[k]:lo[k + 1]], toks[offs[g]:offs[g + 1]])
+            seen.extend(ids.tolist())
+            totals.append(int(lo[-1]))
+        assert sorted(seen) == list(range(1001))
+        assert max(totals) <= 1.01 * (sum(totals) / world) + 500
