@@ -62,3 +62,25 @@ def test_option_constants_match_the_header():
         py = "OPT_" + name[len("MLI_OPT_"):]
         assert getattr(capi, py) == value, f"{py} != {name}"
         assert getattr(mli, py) == value, f"{py} is not exported by the package"
+
+
+def test_comm_and_engine_argument_errors_need_no_gpu():
+    """contract violations are reported before anything touches a device; the multi-GPU entry points cite why
+    the reference has nothing for them to replace"""
+    lib = capi.load_library()
+    small = C.create_string_buffer(8)
+    assert lib.mli_comm_get_unique_id(small, 8) == -2          # MLI_ERR_ARG: buffer shorter than MLI_COMM_ID_BYTES
+    assert b"MLI_COMM_ID_BYTES" in lib.mli_last_error()
+    out = C.c_void_p()
+    assert lib.mli_comm_init_rank(None, 2, 0, small, C.byref(out)) == -2      # null context
+    assert lib.mli_comm_gather_tokens(None, None, 1, None, None) == -2
+    assert lib.mli_engine_submit(None, 0, None, None, 0) == -2
+    assert lib.mli_engine_enqueue(None, 0, None, None, 0, None) == -2
+    n = C.c_int()
+    assert lib.mli_engine_poll_finished(None, 0, None, None, None, 0, C.byref(n)) == -2
+    comm = HEADER[HEADER.index("multi-GPU: request sharding"):HEADER.index("#define MLI_COMM_ID_BYTES")]
+    assert "include/inferencer.h:23-32" in comm and "single-GPU" in comm
+    for name in ("mli_engine_enqueue", "mli_engine_poll_finished"):
+        decl = HEADER.index("int " + name + "(")
+        comment = HEADER[HEADER.rindex("/*", 0, decl):decl]
+        assert re.search(r"\.(cu|cpp|h):\d+", comment), f"{name}: no reference file:line cited"
