@@ -62,6 +62,7 @@ def engine_case(ctx, mode, name):
     eng.run()
     eng.enqueue((offs[8:] - offs[8]).astype(np.int32), toks[offs[8]:])
     eng.run()
+    eng.poll_finished()              # arms the device side, returns nothing
     polled, _ = eng.poll_finished()
     got, gorder = eng.results()
     eng.close()
