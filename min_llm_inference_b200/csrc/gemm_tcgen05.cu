@@ -185,6 +185,8 @@ struct TcArgs {
     int trace_slot;
     // persistent launches (bulk plans: split == 1, no deferred reduce): grid = one CTA per SM, work items
     // (feature tile, activation tile) handed out by an atomic counter -- see tc_item()
+    int bn_decode;         // pair kernel: tile width (rows) of a launch WITHOUT prefill granules, chosen on the host so
+                           // that the items fill the CTA pairs in whole rounds; 0 = 256
     int dyn;               // 1 = persistent / dynamic items
     int m_tiles;           // feature tiles of the operand
     int* ctr;              // [2]: next item, CTAs finished (both back at zero when the launch ends)
@@ -783,13 +785,13 @@ __device__ __forceinline__ void st_dsmem_i32(uint32_t addr, int v) {
 }
 
 // items in units of feature-tile PAIRS
-__device__ __forceinline__ TcItems tc_items_pair(const TcArgs& args, int n_valid) {
+__device__ __forceinline__ TcItems tc_items_pair(const TcArgs& args, int n_valid, int bn) {
     TcItems t;
-    const int n_tiles = (n_valid + kMaxBN - 1) / kMaxBN;
+    const int n_tiles = (n_valid + bn - 1) / bn;
     const int m_units = args.m_tiles / 2;
     if (args.mode == TC_STEP) {
         const int pad = (args.counts[0] + 15) & ~15;
-        t.a_tiles = min(n_tiles, (pad + kMaxBN - 1) / kMaxBN);
+        t.a_tiles = min(n_tiles, (pad + bn - 1) / bn);
         t.kv_tiles = args.d / kBM;          // 2 matrices x (d / 128) / 2 pairs
     } else {
         t.a_tiles = n_tiles;
@@ -849,10 +851,17 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             if (args.mode == TC_PREFILL && mat == 1) mat = 2;
         }
     };
-    // first item of the pair = its index (counts are final before this kernel can start, see gemm_tf32x3_kernel)
+    // Tile width of this launch: 256 rows, except that a launch with nothing to prefill (most decode steps, and the
+    // logits) takes the width the host chose so that its items fill the pairs in whole rounds -- e.g. 1024 active
+    // rows x 12 feature pairs are 48 items of 256 rows for 74 pairs (one round, a third of the SMs idle) but 72
+    // items of 192 rows (one round of 3/4 the length).  Uniform over the grid: the scheduler's counts are final
+    // before this kernel can start (see gemm_tf32x3_kernel).
+    const int bn = (args.bn_decode > 0 && (args.mode != TC_STEP || !args.use_gran || args.counts[1] == 0))
+                       ? args.bn_decode : kMaxBN;
+    // first item of the pair = its index
     int item = (int)blockIdx.x >> 1, nt = 0, n_items = 0;
     {
-        const TcItems items = tc_items_pair(args, tc_n_valid(args));
+        const TcItems items = tc_items_pair(args, tc_n_valid(args), bn);
         if (tid == 0) s_items = items;
         n_items = items.n_items;
         if (item < n_items) {
@@ -907,10 +916,10 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             s_next_item[tile_iter & 1] = nxt;
             st_dsmem_i32(dsmem_addr(&s_next_item[tile_iter & 1], 1), nxt);
         }
-        const int n0 = nt * kMaxBN;
-        const int n_eff = min(kMaxBN, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
+        const int n0 = nt * bn;
+        const int n_eff = min(bn, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
         const int n_half = n_eff >> 1;                                // rows this CTA converts
-        if (tid < kMaxBN) {
+        if (tid < bn) {
             const RowIO io = row_io(args, n0 + tid, n_valid, mat, f0);
             src_tab[tid] = io.src;
             dst_tab[tid] = io.dst;
@@ -1374,11 +1383,27 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
         args.dyn = 1;
     }
     // ... and on CTA pairs (cta_group::2) when the feature tiles pair up: emb_dim a multiple of 256
+    args.bn_decode = 0;
     const bool pair = args.dyn && m_tiles % 2 == 0 && (args.mode == TC_LOGITS || (args.d / kBM) % 2 == 0) &&
                       args.n_acc * args.acc_stride <= 512 && !getenv("MLI_TC_NO_PAIR");
     if (pair) {
         int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_pair_kernel, tc_smem_bytes(kPairStages, kPairHalf));
         if (rc0) return rc0;
+        // tile width of launches without prefill granules: the multiple of 32 rows in [128, 256] that minimises
+        // (rounds over the pairs) x (width) for the rows the host expects (all B rows active)
+        const int pairs = ctx->num_sms / 2;
+        const int units = (args.mode == TC_STEP) ? 3 * (args.d / kBM) / 2 : m_tiles / 2;
+        long long best = -1;
+        for (int w = kMaxBN; w >= 128; w -= 32) {
+            const long long tiles = (plan_rows + w - 1) / w;
+            const long long rounds = (tiles * units + pairs - 1) / pairs;
+            const long long cost = rounds * w;
+            if (best < 0 || cost < best) {
+                best = cost;
+                args.bn_decode = w;
+            }
+        }
+        if (args.mode == TC_PREFILL || getenv("MLI_TC_FIXED_TILE")) args.bn_decode = 0;   // prefill tiles stay 256 wide
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = args.dyn ? dim3((unsigned)(pair ? (ctx->num_sms & ~1) : ctx->num_sms), 1u, 1u)
