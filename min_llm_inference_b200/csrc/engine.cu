@@ -898,35 +898,45 @@ int check_host_prompts(const mli_engine* e, int n_req, const int* offs) {
 }
 
 // stage (host prompts) and append requests [first, first + n_req) on `st`, then publish the new total.
-// Caller holds e->mu.
+// Caller holds e->mu.  own_staging = true (mli_engine_enqueue: may run while ANOTHER thread is capturing or
+// replaying the step graph on the engine's stream): the staging buffer is a stream-ordered allocation on `st`,
+// so nothing here synchronises the device or touches the engine's stream; false (mli_engine_submit, on the
+// engine's stream itself): the engine's persistent staging buffer.
 int append_requests(mli_engine* e, int first, int n_req, const int* offs, const int* toks, int is_device,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool own_staging) {
     if (n_req <= 0) return 0;
     const int* d_offs = offs;
     const int* d_toks = toks;
+    int* tmp = nullptr;
     if (!is_device) {
         const int total = offs[n_req] - offs[0];
         const size_t need = (size_t)n_req + 1 + (size_t)total;
-        if (e->stage_ints < need) {
-            // the previous staging buffer may still be read by an earlier append
-            MLI_CUDA(cudaStreamSynchronize(e->stream));
-            MLI_CUDA(cudaStreamSynchronize(e->ingest));
-            if (e->stage_buf) cudaFree(e->stage_buf);
-            e->stage_buf = nullptr;
-            e->stage_ints = 0;
-            MLI_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->stage_buf), sizeof(int) * need));
-            e->stage_ints = need;
+        int* buf = nullptr;
+        if (own_staging) {
+            MLI_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), sizeof(int) * need, st));
+            buf = tmp;
+        } else {
+            if (e->stage_ints < need) {
+                MLI_CUDA(cudaStreamSynchronize(st));   // an earlier submit may still read the old buffer
+                if (e->stage_buf) cudaFree(e->stage_buf);
+                e->stage_buf = nullptr;
+                e->stage_ints = 0;
+                MLI_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->stage_buf), sizeof(int) * need));
+                e->stage_ints = need;
+            }
+            buf = e->stage_buf;
         }
-        MLI_CUDA(cudaMemcpyAsync(e->stage_buf, offs, sizeof(int) * ((size_t)n_req + 1), cudaMemcpyHostToDevice, st));
-        MLI_CUDA(cudaMemcpyAsync(e->stage_buf + n_req + 1, toks + offs[0], sizeof(int) * (size_t)total,
+        MLI_CUDA(cudaMemcpyAsync(buf, offs, sizeof(int) * ((size_t)n_req + 1), cudaMemcpyHostToDevice, st));
+        MLI_CUDA(cudaMemcpyAsync(buf + n_req + 1, toks + offs[0], sizeof(int) * (size_t)total,
                                  cudaMemcpyHostToDevice, st));
-        d_offs = e->stage_buf;
-        d_toks = e->stage_buf + n_req + 1 - offs[0];   // the kernel indexes tokens with the caller's offsets
+        d_offs = buf;
+        d_toks = buf + n_req + 1 - offs[0];   // the kernel indexes tokens with the caller's offsets
     }
     engine_append_kernel<<<n_req, 128, 0, st>>>(e->a, d_offs, d_toks, first, n_req);
     MLI_LAUNCH_CHECK();
     engine_publish_kernel<<<1, 1, 0, st>>>(e->a, first + n_req);
     MLI_LAUNCH_CHECK();
+    if (tmp) MLI_CUDA(cudaFreeAsync(tmp, st));
     return 0;
 }
 
@@ -1148,7 +1158,7 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
     e->done_host[0] = 0;
     engine_reset_kernel<<<64, 256, 0, ctx->stream>>>(e->a, e->pool, page_floats, e->cfg.max_requests);
     MLI_LAUNCH_CHECK();
-    if ((rc = append_requests(e, 0, n_req, prompt_offsets, prompt_tokens, is_device, ctx->stream))) return rc;
+    if ((rc = append_requests(e, 0, n_req, prompt_offsets, prompt_tokens, is_device, ctx->stream, false))) return rc;
     MLI_CUDA(cudaEventRecord(e->reset_ev, ctx->stream));
     e->n_req = n_req;
     e->n_polled = 0;
@@ -1169,8 +1179,8 @@ int mli_engine_enqueue(mli_engine* e, int n_req, const int* prompt_offsets, cons
     MLI_REQUIRE(e->n_req + n_req <= e->cfg.max_requests, "request table full (mli_engine_cfg.max_requests)");
     // on the ingest stream, concurrent with the step graphs; ordered after the last reset only
     MLI_CUDA(cudaStreamWaitEvent(e->ingest, e->reset_ev, 0));
-    if ((rc = append_requests(e, e->n_req, n_req, prompt_offsets, prompt_tokens, is_device, e->ingest))) return rc;
-    // the caller may reuse its buffers, and the next append may reuse the staging buffer
+    if ((rc = append_requests(e, e->n_req, n_req, prompt_offsets, prompt_tokens, is_device, e->ingest, true))) return rc;
+    // the caller may reuse its buffers as soon as this returns
     MLI_CUDA(cudaStreamSynchronize(e->ingest));
     if (first_id) *first_id = e->n_req;
     e->n_req += n_req;

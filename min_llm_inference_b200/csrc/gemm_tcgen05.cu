@@ -551,7 +551,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 rp[i] = p ? reinterpret_cast<const float4*>(p) + chunk : nullptr;
             }
             // two register sets (even / odd k-blocks): the loads of k-block kb+2 are in flight while
-            // k-block kb+1 is converted, so global latency is off the per-stage critical path
+            // k-block kb+1 is converted, so global latency is off the per-stage critical path.  (The pair kernel's
+            // scheme -- two warp groups on alternate k-blocks, nothing in flight when a stage is published -- was
+            // measured here too: with only K/split = 8 k-blocks per CTA it loses, 20.0 vs 17.9 us per launch.)
             float4 ra[kMaxBN / 32], rb[kMaxBN / 32];
             auto load_set = [&](float4 (&dst)[kMaxBN / 32], int kb) {
 #pragma unroll

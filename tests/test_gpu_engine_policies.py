@@ -210,26 +210,36 @@ def test_enqueue_and_poll_stream_requests(torch_cuda, ctx, gemm_mode):
 
         eng = make_engine(ctx, torch, cfg, w, cfg["n_req"])
         eng.submit(*part(0, 12))
-        got, seen = {}, []
+        got, seen, errors_in_threads = {}, [], []
         stop = threading.Event()
 
         def feeder():
-            assert eng.enqueue(*part(12, 24)) == 12
+            try:
+                assert eng.enqueue(*part(12, 24)) == 12
+            except Exception as exc:   # a worker's failure must fail the test, not vanish with the thread
+                errors_in_threads.append(exc)
 
         def poller():
-            while not stop.is_set():
-                r, ids = eng.poll_finished(max_out=5)
-                got.update(r)
-                seen.extend(ids.tolist())
+            try:
+                while not stop.is_set():
+                    r, ids = eng.poll_finished(max_out=5)
+                    got.update(r)
+                    seen.extend(ids.tolist())
+            except Exception as exc:
+                errors_in_threads.append(exc)
 
         t1, t2 = threading.Thread(target=feeder), threading.Thread(target=poller)
-        t2.start(); t1.start()
-        eng.run()
-        t1.join()
-        eng.run()                      # the second wave may have landed after the first run went idle
-        assert eng.enqueue(*part(24, 36)) == 24
-        eng.run()
-        stop.set(); t2.join()
+        try:
+            t2.start(); t1.start()
+            eng.run()                      # (the first run also CAPTURES the step graph while the two threads work)
+            t1.join()
+            eng.run()                      # the second wave may have landed after the first run went idle
+            assert eng.enqueue(*part(24, 36)) == 24
+            eng.run()
+        finally:
+            stop.set()
+            t1.join(); t2.join()           # nobody may still use the engine when it is destroyed
+        assert not errors_in_threads, errors_in_threads
         # drain (the first poll after a submit only arms the device side and returns nothing)
         for _ in range(200):
             if len(seen) == cfg["n_req"]:
