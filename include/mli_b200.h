@@ -231,6 +231,15 @@ typedef struct {
                                   over several steps instead of stalling every decoding row behind one
                                   huge prefill GEMM (the reference admits everything that fits,
                                   src/paged_item_storage.cpp:84-113) */
+    int prefill_chunk_positions; /* > 0: chunked prefill: a step prefills at most this many prompt
+                                  positions (a multiple of 16) over all rows whose prompts are still being
+                                  prefilled, in admission order; an admitted row stays inactive until the step
+                                  that schedules its last chunk, in which it also emits its first token -- the
+                                  decoding rows are never stalled behind one huge prefill GEMM (the reference
+                                  prefills a whole prompt in the step that admits it, src/inference_model.cpp:
+                                  52-82).  Tokens do not depend on the chunking; needs compat_stale_lengths = 0.
+                                  Tensor-core mode computes the chunks step by step; exact-order mode keeps the
+                                  same schedule but prefills a row when it becomes active */
 } mli_engine_cfg;
 
 typedef struct {

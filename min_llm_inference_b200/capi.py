@@ -38,7 +38,7 @@ class EngineCfg(C.Structure):
         ("n_batch", _I), ("n_sequence", _I), ("emb_dim", _I), ("n_vocab", _I),
         ("n_blocks", _I), ("n_forward_rounds", _I), ("compat_stale_lengths", _I),
         ("max_requests", _I), ("page_pool", _P),
-        ("max_new_tokens", _I), ("max_prefill_positions", _I),
+        ("max_new_tokens", _I), ("max_prefill_positions", _I), ("prefill_chunk_positions", _I),
     ]
 
 

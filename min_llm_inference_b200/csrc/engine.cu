@@ -68,6 +68,9 @@ struct SchedArgs {
     int B, S, W, R, n_blocks, compat;
     int max_new;      // > 0: a request is finished once it has generated this many tokens (opt-in)
     int max_prefill;  // > 0: admission throttle, prompt positions admitted per step (opt-in)
+    int chunk;        // > 0: chunked prefill (opt-in): prompt positions prefilled per step, a multiple
+                      // of 16; an admitted row stays inactive (length 0) until its last chunk is scheduled
+    int* pf_pos;      // [B] chunked prefill: positions of the row's prompt already scheduled, -1 = not prefilling
 };
 
 constexpr int kSchedThreads = 1024;
@@ -199,6 +202,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             for (int j = 0; j < R; ++j) {
                 const int t = a.dec[(size_t)r * R + j];
                 if (t == MLI_EMPTY_ROW_TOKEN_ID) {
+                    // a row whose prompt is still being prefilled in chunks has no token yet and is NOT free
+                    if (a.chunk > 0 && id >= 0 && a.pf_pos[r] >= 0) break;
                     empty = true;
                 } else if (id < 0) {
                     local_err = 1;  // token for a row that is not processing
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                     qh = (qh - 1 + q_cap) % q_cap;
                     a.queue[qh] = s_req[row];   // (the queue count is adjusted by every thread below)
                     s_req[row] = -1;
+                    if (a.chunk > 0) a.pf_pos[row] = -1;   // a pre-empted prompt starts over when it is re-admitted
                     const int np = s_np[row];
                     for (int t = 0; t < np; ++t) {
                         float* pg = a.page_table[(size_t)row * W + t];
@@ -458,8 +464,16 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
                         (wi < n_fq) ? fq[wi] : a.free_ring[(fh + before + t) % nb];
                 }
                 s_np[row] = take;
-                s_len[row] = len;
-                a.lengths[row] = len;
+                if (a.chunk > 0) {
+                    // chunked prefill: the row becomes active (length = prompt length) in the step that
+                    // schedules its last chunk (below); until then the model kernels see an empty row
+                    s_len[row] = 0;
+                    a.lengths[row] = 0;
+                    a.pf_pos[row] = 0;
+                } else {
+                    s_len[row] = len;
+                    a.lengths[row] = len;
+                }
                 a.len_shadow[row] = len;
                 s_req[row] = id;
                 s_used[n_used + j] = row;
@@ -505,6 +519,54 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
     }
     for (int i = tid; i < n_used; i += T) a.used[i] = s_used[i];
 
+    // ================= chunked prefill (opt-in): this step's share of the prompts still being prefilled =====
+    // Rows in admission order (the used list) take 16-position granules of their remaining prompt until the
+    // step's budget is spent -- a prefix fill decided by one scan.  A row whose last granule is scheduled here
+    // becomes active in this very step: the merged projection computes its granules and its latest-token q/K/V
+    // in one launch, the attention that follows sees all of it.
+    int n_gran_chunk = 0, n_done_chunk = 0;
+    if (a.chunk > 0) {
+        const int budget = a.chunk / kGran;
+        int g_before = 0;
+        for (int base = 0; base < n_used; base += T) {
+            const int i = base + tid;
+            int row = -1, p = -1, L = 0, g_rem = 0;
+            if (i < n_used) {
+                row = s_used[i];
+                p = a.pf_pos[row];
+                if (p >= 0) {
+                    L = a.len_shadow[row];
+                    g_rem = (L - p + kGran - 1) / kGran;
+                }
+            }
+            int tot;
+            const int before = g_before + block_scan_excl(g_rem, &tot, s_warp, scan_phase);
+            const int take = max(0, min(g_rem, budget - before));
+            const int done = (p >= 0 && take == g_rem) ? 1 : 0;
+            int totd;
+            const int dpos = n_done_chunk + block_scan_excl(done, &totd, s_warp, scan_phase);
+            if (take > 0 || done) {
+                for (int c = 0; c < take; ++c)
+                    if (before + c < a.max_gran) {
+                        a.gran[before + c].row = row;
+                        a.gran[before + c].j0 = p + c * kGran;
+                    }
+                if (done) {
+                    s_len[row] = L;
+                    a.lengths[row] = L;
+                    a.pf_pos[row] = -1;
+                    a.new_idx[dpos] = row;   // (exact-order mode prefills a whole row when it becomes active)
+                } else {
+                    a.pf_pos[row] = p + take * kGran;
+                }
+            }
+            g_before += tot;
+            n_done_chunk += totd;
+        }
+        n_gran_chunk = min(g_before, budget);
+        __syncthreads();
+    }
+
     // ---- work lists of this step: active rows, prefill granules of the new rows ----
     int n_act = 0;
     for (int base = 0; base < B; base += T) {
@@ -516,7 +578,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         n_act += tot;
     }
     int n_gran = 0;
-    for (int base = 0; base < k_adm; base += T) {
+    for (int base = 0; base < k_adm && a.chunk <= 0; base += T) {
         const int j = base + tid;
         int row = -1, n = 0;
         if (j < k_adm) {
@@ -542,7 +604,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         v->q_head = qh;
         v->q_count = qc;
         v->n_used = n_used;
-        v->n_new = k_adm;
+        v->n_new = (a.chunk > 0) ? n_done_chunk : k_adm;
         v->admitted = sv.admitted + k_adm;
         v->preemptions = sv.preemptions;
         v->iter = sv.iter + 1;
@@ -556,6 +618,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
         v->n_req = n_avail;
         v->max_used = max(sv.max_used, n_used);
         v->min_free = min(sv.min_free, F);
+        if (a.chunk > 0) n_gran = n_gran_chunk;
         a.counts[0] = n_act;
         a.counts[1] = min(n_gran, a.max_gran);
         if (a.trace != nullptr && a.trace[0] >= 1 && a.trace[0] - 1 < a.trace[1]) {
@@ -588,6 +651,7 @@ __global__ void engine_reset_kernel(SchedArgs a, float* pool, size_t page_floats
         a.len_shadow[r] = 0;
         a.npages[r] = 0;
         a.new_idx[r] = 0;
+        a.pf_pos[r] = -1;
         for (int j = 0; j < a.R; ++j) a.dec[(size_t)r * a.R + j] = MLI_EMPTY_ROW_TOKEN_ID;
     }
     for (int b = i; b < a.n_blocks; b += n) a.free_ring[b] = pool + (size_t)b * page_floats;
@@ -780,9 +844,11 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t g
     if (tc) {
         // tensor-core mode: the scheduler already listed the active rows and the 16-position prefill
         // granules of the new rows; encoder -> ONE merged projection (latest K,q,V + prefill K,V)
+        // (chunked prefill: a row that is still prefilling has length 0; its granules are bounded by the
+        // admission length the scheduler keeps in len_shadow)
         if ((rc = launch_paged_encoder_tiles(ctx, e->emb, e->pos, nullptr, e->a.row_req, e->a.req_tok,
                                              e->a.page_table, e->a.gran, e->a.counts + 1, e->a.max_gran,
-                                             e->a.lengths, S, d, kPage)))
+                                             e->a.chunk > 0 ? e->a.len_shadow : e->a.lengths, S, d, kPage)))
             return rc;
     } else {
         if ((rc = launch_build_new_row_tiles(ctx, e->a.new_idx, e->a.lengths, 0, &e->a.v->n_new, e->tiles,
@@ -804,7 +870,7 @@ int enqueue_model(mli_engine* e, cudaEvent_t ev0, cudaEvent_t ev1, cudaEvent_t g
             }
             rc = launch_step_qkv_tc(ctx, e->a.page_table, e->a.lengths, e->a.act_rows, e->a.counts,
                                     e->a.gran, e->a.max_gran, round == 0 ? 1 : 0, e->wk, e->wq, e->wv,
-                                    e->q_out, B, S, d);
+                                    e->q_out, B, S, d, e->a.chunk > 0 ? e->a.len_shadow : nullptr);
             ctx->gemm_ev_start = ctx->gemm_ev_stop = nullptr;
         }
         else
@@ -997,7 +1063,10 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
                 "bad engine dims");
     MLI_REQUIRE(cfg->n_forward_rounds >= 1 && cfg->n_forward_rounds <= kPage,
                 "n_forward_rounds must be 1..16");
-    MLI_REQUIRE(cfg->max_new_tokens >= 0 && cfg->max_prefill_positions >= 0, "negative policy value");
+    MLI_REQUIRE(cfg->max_new_tokens >= 0 && cfg->max_prefill_positions >= 0 && cfg->prefill_chunk_positions >= 0,
+                "negative policy value");
+    MLI_REQUIRE(cfg->prefill_chunk_positions == 0 || (cfg->prefill_chunk_positions >= kPage && !cfg->compat_stale_lengths),
+                "prefill_chunk_positions must be 0 or >= 16, and needs corrected lengths (compat_stale_lengths = 0)");
     MLI_REQUIRE(sched_smem_bytes(cfg->n_batch) <= 220 * 1024,
                 "n_batch too large for the device scheduler's shared-memory mirrors (max ~10000 rows per GPU)");
     {
@@ -1015,6 +1084,7 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     a.compat = cfg->compat_stale_lengths;
     a.max_new = cfg->max_new_tokens;
     a.max_prefill = cfg->max_prefill_positions;
+    a.chunk = cfg->prefill_chunk_positions / kPage * kPage;
     int rc = 0;
 #define A(call) if ((rc = (call))) { mli_engine_destroy(e); return rc; }
     A(dev_alloc(e, &a.v, 1));
@@ -1032,6 +1102,7 @@ int mli_engine_create(mli_ctx* ctx, const mli_engine_cfg* cfg, const float* emb_
     A(dev_alloc(e, &a.free_ring, cfg->n_blocks));
     A(dev_alloc(e, &a.dec, (size_t)B * R));
     A(dev_alloc(e, &a.new_idx, B));
+    A(dev_alloc(e, &a.pf_pos, B));
     A(dev_alloc(e, &a.act_rows, B));
     a.max_gran = B * W;
     A(dev_alloc(e, &a.gran, (size_t)a.max_gran));

@@ -170,6 +170,7 @@ struct TcArgs {
     const int* act;        // LOGITS (optional) / STEP: compact list of active rows
     const int* counts;     // [0] = active rows, [1] = granules (device-side)
     const TileDesc* gran;  // STEP: 16-position prefill granules of the new rows
+    const int* gran_bound; // STEP: per-row prompt length bounding the granules (chunked prefill); NULL = lengths
     int use_gran;
     int kv_bf16;           // compact page format: K and V rows are stored as bf16
     int defer;             // LOGITS: every split rank stores its partial plane (no cross-CTA reduce)
@@ -315,7 +316,7 @@ __device__ __forceinline__ RowIO row_io(const TcArgs& args, int n, int n_valid, 
             const TileDesc t = args.gran[(n - pad) / kGranM];
             r = t.row;
             j = t.j0 + ((n - pad) % kGranM);
-            if (j >= args.lengths[r] - 1) return io;
+            if (j >= (args.gran_bound ? args.gran_bound[r] : args.lengths[r]) - 1) return io;
             latest = false;
             if (mat == 1) return io;   // no q for prefill positions
         }
@@ -1524,7 +1525,7 @@ int launch_prefill_kv_paged_tc(mli_ctx* ctx, float* const* page_table, const Til
 int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* lengths, const int* act_rows,
                        const int* counts, const TileDesc* gran, int max_gran, int use_gran,
                        const float* wk, const float* wq, const float* wv, float* q_output, int B, int S,
-                       int d) {
+                       int d, const int* gran_bound) {
     if (!shapes_ok(d, d)) {
         set_error("tcgen05 step projection: emb_dim must be a multiple of 128");
         return MLI_ERR_UNSUPPORTED;
@@ -1536,6 +1537,7 @@ int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* length
     a.mode = TC_STEP; a.K = d; a.d = d; a.page_table = page_table; a.lengths = lengths;
     a.q_out = q_output; a.W = S / kPage; a.B = B; a.act = act_rows; a.counts = counts; a.gran = gran;
     a.use_gran = use_gran;
+    a.gran_bound = gran_bound;
     const long long bound = (long long)((B + 15) / 16 * 16) + (use_gran ? (long long)max_gran * kGranM : 0);
     a.n_rows = (int)std::min<long long>(bound, 1 << 30);
     // a step usually has at most B active rows plus a few short prompts: plan the split for that

@@ -72,7 +72,7 @@ int launch_logits_tc(mli_ctx* ctx, const float* attn, const float* emb, float* p
 int launch_step_qkv_tc(mli_ctx* ctx, float* const* page_table, const int* lengths, const int* act_rows,
                        const int* counts, const TileDesc* gran, int max_gran, int use_gran,
                        const float* wk, const float* wq, const float* wv, float* q_output, int B, int S,
-                       int d);
+                       int d, const int* gran_bound = nullptr);
 
 // ---- fused decode attention --------------------------------------------------------------------
 int launch_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_table,

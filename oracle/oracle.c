@@ -529,13 +529,15 @@ static void emit_finished(const req_store* rs, int* finished_ids, int* finished_
  * Returns number of finished_indices written; *phantom is set if a token arrives for a row that
  * is not processing (the reference would default-construct an entry there, :117). */
 static int process_decoder_result(const int* dec, int B, int R, int S, req_store* rs, int* row_req,
-                                  int* finished_indices, long long* gen, int* phantom) {
+                                  int* finished_indices, long long* gen, int* phantom, const int* pf_pos) {
     int nf = 0;
     for (int i = 0; i < B; ++i) {
         int empty = 0, finished = 0;
         for (int j = 0; j < R; ++j) {
             int t = dec[(size_t)i * R + j];
             if (t == ORC_EMPTY_TOKEN) {
+                /* chunked prefill: a row whose prompt is still being prefilled has no token yet and is not free */
+                if (pf_pos && row_req[i] >= 0 && pf_pos[i] >= 0) break;
                 empty = 1;
             } else {
                 int id = row_req[i];
@@ -574,6 +576,10 @@ typedef struct {
     int needs_sync;
     int *inp_host, *inp_dev, *len_host, *len_dev, *idx_host, *idx_dev;
     int* row_req;
+    /* opt-in chunked prefill of the product's engine (not in the reference; 0 = off) */
+    int chunk;            /* prompt positions prefilled per step (multiple of 16) */
+    int* pf_pos;          /* [B] positions of the row's prompt already scheduled, -1 = not prefilling */
+    int* pf_len;          /* [B] prompt length of a prefilling row */
 } paged_state;
 
 static float* page_ptr(const paged_state* ps, int id) {
@@ -599,6 +605,7 @@ static void used_erase_at(paged_state* ps, int pos) {
 static void move_to_new(paged_state* ps, req_store* rs, int row) { /* item_storage.cpp:75-79 */
     rs_push_front(rs, ps->row_req[row]);
     ps->row_req[row] = -1;
+    if (ps->pf_pos) ps->pf_pos[row] = -1; /* a pre-empted prompt starts over when it is re-admitted */
 }
 
 /* src/paged_item_storage.cpp:14-60 (allocate_or_free_memory_blocks_if_needed) */
@@ -659,6 +666,7 @@ static int paged_insert_new_items(paged_state* ps, req_store* rs, int fix_stale_
                                   int max_prefill) {
     int B = ps->B, S = ps->S, W = ps->W, R = ps->R;
     int admitted_positions = 0; /* opt-in admission throttle (not in the reference; 0 = off) */
+    int n_admitted_chunk = 0;   /* chunk mode: admissions of this call (they are not "new items" yet) */
     char* occ = (char*)calloc((size_t)B, 1);
     for (int p = 0; p < ps->n_used; ++p) occ[ps->used_rows[p]] = 1;
     if (fix_stale_lengths) memcpy(ps->len_host, ps->len_dev, sizeof(int) * (size_t)B);
@@ -667,13 +675,21 @@ static int paged_insert_new_items(paged_state* ps, req_store* rs, int fix_stale_
         if (occ[i]) continue;
         if (ps->fcount >= ORC_INIT_BLOCKS && rs->qcount > 0 &&
             ps->fcount >= ceil_div_i(rs_head_len(rs) + R, ORC_PAGE_BLOCK) &&
-            (max_prefill <= 0 || n_new == 0 || admitted_positions + rs_head_len(rs) <= max_prefill)) {
+            (max_prefill <= 0 || n_new + n_admitted_chunk == 0 ||
+             admitted_positions + rs_head_len(rs) <= max_prefill)) {
             int id = rs_pop_front(rs);
             int len = rs->cnt[id];
             admitted_positions += len;
-            ps->len_host[i] = len;
             memcpy(ps->inp_host + (size_t)i * S, rs->tok + (size_t)id * S, sizeof(int) * (size_t)len);
-            ps->idx_host[n_new++] = i;
+            if (ps->chunk > 0) { /* inactive until its last chunk is scheduled (plan_prefill_chunks) */
+                ps->len_host[i] = 0;
+                ps->pf_pos[i] = 0;
+                ps->pf_len[i] = len;
+                n_admitted_chunk++;
+            } else {
+                ps->len_host[i] = len;
+                ps->idx_host[n_new++] = i;
+            }
             int nb = ceil_div_i(len + R, ORC_PAGE_BLOCK);
             if (nb < ORC_INIT_BLOCKS) nb = ORC_INIT_BLOCKS;
             ps->row_req[i] = id;
@@ -709,6 +725,33 @@ static int paged_insert_new_items(paged_state* ps, req_store* rs, int fix_stale_
     return n_new;
 }
 
+/* Chunked prefill (opt-in policy of the product's engine, csrc/engine.cu; the reference prefills a whole prompt in
+ * the step that admits it): rows in admission order take 16-position granules of their remaining prompt until
+ * the step's budget is spent.  A row whose last granule is scheduled becomes active in this step -- it is
+ * appended to the new-item list, so the forward below prefills it (K and V do not depend on how the positions
+ * were cut into chunks) and emits its first token.  Returns the number of rows that became active. */
+static int plan_prefill_chunks(paged_state* ps, int n_new) {
+    int budget = ps->chunk / ORC_PAGE_BLOCK;
+    for (int p = 0; p < ps->n_used && budget > 0; ++p) {
+        int row = ps->used_rows[p];
+        if (ps->pf_pos[row] < 0) continue;
+        int g_rem = ceil_div_i(ps->pf_len[row] - ps->pf_pos[row], ORC_PAGE_BLOCK);
+        int take = g_rem < budget ? g_rem : budget;
+        budget -= take;
+        if (take == g_rem) {
+            ps->pf_pos[row] = -1;
+            ps->len_host[row] = ps->pf_len[row];
+            ps->len_dev[row] = ps->pf_len[row];
+            ps->idx_dev[n_new] = row;
+            ps->idx_host[n_new] = row;
+            n_new++;
+        } else {
+            ps->pf_pos[row] += take * ORC_PAGE_BLOCK;
+        }
+    }
+    return n_new;
+}
+
 /* src/inferencer.cpp:43-85 (start_paged_attention_inference_engine) */
 int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
                          const float* pos_table, const float* wk, const float* wq,
@@ -738,6 +781,13 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
     ps.idx_dev = (int*)calloc((size_t)B, sizeof(int));
     ps.row_req = (int*)malloc(sizeof(int) * (size_t)B);
     for (int i = 0; i < B; ++i) ps.row_req[i] = -1;
+    ps.chunk = cfg->prefill_chunk_positions / ORC_PAGE_BLOCK * ORC_PAGE_BLOCK;
+    if (ps.chunk > 0 && !cfg->fix_stale_lengths) return -1; /* needs corrected lengths */
+    if (ps.chunk > 0) {
+        ps.pf_pos = (int*)malloc(sizeof(int) * (size_t)B);
+        ps.pf_len = (int*)calloc((size_t)B, sizeof(int));
+        for (int i = 0; i < B; ++i) ps.pf_pos[i] = -1;
+    }
     req_store rs;
     rs_init(&rs, n_req, S, prompt_offsets, prompt_tokens);
     int* dec = (int*)malloc(sizeof(int) * (size_t)B * R);
@@ -749,6 +799,7 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
 
     rs.max_new = cfg->max_new_tokens;
     int n_new = paged_insert_new_items(&ps, &rs, cfg->fix_stale_lengths, cfg->max_prefill_positions);
+    if (ps.chunk > 0) n_new = plan_prefill_chunks(&ps, n_new);
     for (;;) {
         int processing = 0;
         for (int i = 0; i < B; ++i) processing += (ps.row_req[i] >= 0);
@@ -757,10 +808,11 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
         orc_paged_forward(ps.inp_dev, ps.len_dev, ps.idx_dev, dec, n_new, emb_table, pos_table,
                           ps.pt_dev, wk, wq, wv, attn, score, B, S, d, V, R);
         int nf = process_decoder_result(dec, B, R, S, &rs, ps.row_req, finished_indices, &gen,
-                                        &phantom);
+                                        &phantom, ps.pf_pos);
         if (phantom) { rc = -3; break; }
         allocate_or_free(&ps, &rs, finished_indices, nf, &pre);
         n_new = paged_insert_new_items(&ps, &rs, cfg->fix_stale_lengths, cfg->max_prefill_positions);
+        if (ps.chunk > 0) n_new = plan_prefill_chunks(&ps, n_new);
         ++steps;
     }
     emit_finished(&rs, finished_ids, finished_offsets, finished_tokens);
@@ -773,6 +825,7 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
     free(ps.slab); free(ps.freeq); free(ps.used_rows); free(ps.row_pages); free(ps.row_npages);
     free(ps.pt_host); free(ps.pt_dev); free(ps.inp_host); free(ps.inp_dev); free(ps.len_host);
     free(ps.len_dev); free(ps.idx_host); free(ps.idx_dev); free(ps.row_req);
+    free(ps.pf_pos); free(ps.pf_len);
     return rc;
 }
 
@@ -826,7 +879,7 @@ int orc_dense_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
         if (cfg->max_steps > 0 && steps >= cfg->max_steps) { rc = -4; break; }
         orc_dense_forward(inp, len, idx, dec, n_new, emb_table, pos_table, wk, wq, wv, emb, kt, vc,
                           B, S, d, V);
-        nf = process_decoder_result(dec, B, 1, S, &rs, row_req, finished_indices, &gen, &phantom);
+        nf = process_decoder_result(dec, B, 1, S, &rs, row_req, finished_indices, &gen, &phantom, NULL);
         if (phantom) { rc = -3; break; }
         ++steps;
     }

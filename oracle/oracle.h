@@ -124,6 +124,9 @@ typedef struct {
     int max_new_tokens;        /* > 0: a request is finished once it has generated this many tokens */
     int max_prefill_positions; /* > 0: one insert_new_items call admits prompts only while their
                                   positions add up to at most this many (the first always passes) */
+    int prefill_chunk_positions; /* > 0: chunked prefill -- a step schedules at most this many prompt positions
+                                  (granules of 16, rows in admission order); an admitted row becomes active in
+                                  the step that schedules its last chunk.  Needs fix_stale_lengths = 1 */
 } orc_engine_cfg;
 
 typedef struct {

@@ -30,7 +30,8 @@ _P, _I = C.c_void_p, C.c_int
 class OrcCfg(C.Structure):
     _fields_ = [("n_batch", _I), ("n_sequence", _I), ("emb_dim", _I), ("n_vocab", _I),
                 ("n_blocks", _I), ("n_forward_rounds", _I), ("fix_stale_lengths", _I),
-                ("max_steps", _I), ("max_new_tokens", _I), ("max_prefill_positions", _I)]
+                ("max_steps", _I), ("max_new_tokens", _I), ("max_prefill_positions", _I),
+                ("prefill_chunk_positions", _I)]
 
 
 class OrcStats(C.Structure):
@@ -206,7 +207,7 @@ def run_oracle_engine(kind, cfg: dict, w, offs, toks, fix=0, max_steps=0, thread
     n_req = len(offs) - 1
     S = cfg["S"]
     c = OrcCfg(cfg["B"], S, cfg["d"], cfg["V"], cfg.get("n_blocks", 0), cfg.get("R", 1), fix, max_steps,
-               cfg.get("max_new", 0), cfg.get("max_prefill", 0))
+               cfg.get("max_new", 0), cfg.get("max_prefill", 0), cfg.get("chunk", 0))
     ids = np.zeros(n_req, np.int32)
     fo = np.zeros(n_req + 1, np.int32)
     ft = np.zeros(n_req * S, np.int32)

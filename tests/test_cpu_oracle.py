@@ -242,3 +242,19 @@ def test_oracle_policy_flags():
     for i in range(15):
         assert np.array_equal(thr[i], base[i])
     assert st_t.steps >= st.steps      # admissions are spread over more iterations
+
+
+def test_oracle_chunked_prefill():
+    """chunked prefill as restated in the oracle: the same token lists as the unchunked job, first tokens later"""
+    cfg = dict(B=4, S=128, d=32, V=1024, n_blocks=48, R=1, max_new=6)
+    w = H.make_weights(21, cfg["d"], cfg["V"], cfg["S"], "Z")
+    offs, toks = H.make_prompts(23, 9, 30, 100)
+    rc, base, _, st = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1)
+    rc2, chunked, _, st_c = H.run_oracle_engine("paged", dict(cfg, chunk=32), w, offs, toks, fix=1)
+    assert rc == 0 and rc2 == 0 and st.n_finished == st_c.n_finished == 9
+    for i in range(9):
+        assert np.array_equal(base[i], chunked[i])
+    assert st_c.steps > st.steps
+    # needs corrected lengths
+    rc3, *_ = H.run_oracle_engine("paged", dict(cfg, chunk=32), w, offs, toks, fix=0)
+    assert rc3 == -1

@@ -26,7 +26,7 @@ def dev(torch, x):
 def make_engine(ctx, torch, cfg, w, max_req, compat=0):
     dw = {k: dev(torch, v) for k, v in w.items()}
     ec = mli.EngineCfg(cfg["B"], cfg["S"], cfg["d"], cfg["V"], cfg["n_blocks"], cfg.get("R", 1), compat, max_req,
-                       None, cfg.get("max_new", 0), cfg.get("max_prefill", 0))
+                       None, cfg.get("max_new", 0), cfg.get("max_prefill", 0), cfg.get("chunk", 0))
     return mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
 
 
@@ -342,3 +342,85 @@ def test_attention_many_rows_coarse_row_table(torch_cuda, ctx, B, min_dyn):
     err = float((out.double() - want).abs().max() / want.abs().max())
     assert err < 1e-4, f"rel err {err:.2e}"
     assert not out[dL == 0].any(), "empty rows must produce zeros"
+
+
+CHUNK_CASES = [
+    # long prompts against a small budget: rows spend several steps prefilling before their first token
+    dict(B=8, S=256, d=128, V=1024, n_blocks=160, n_req=20, lo=40, hi=200, max_new=10, chunk=64),
+    # budget smaller than one granule pair, many rows prefilling at once, pool pressure (a prefilling row can be
+    # pre-empted and starts over), several rounds per step
+    dict(B=12, S=128, d=128, V=1024, n_blocks=70, n_req=40, lo=10, hi=100, max_new=12, chunk=32, R=2),
+    # budget larger than most prompts: several rows complete in one step; combined with the admission throttle
+    dict(B=16, S=128, d=256, V=1024, n_blocks=160, n_req=48, lo=5, hi=90, max_new=8, chunk=256, max_prefill=200),
+    # runs to n_sequence (no token cap)
+    dict(B=6, S=64, d=128, V=1024, n_blocks=30, n_req=14, lo=8, hi=50, chunk=16),
+]
+
+
+@pytest.mark.parametrize("gemm_mode", [mli.GEMM_SIMT_EXACT, mli.GEMM_TCGEN05], ids=["exact", "tcgen05"])
+@pytest.mark.parametrize("cfg", CHUNK_CASES, ids=lambda c: f"chunk{c['chunk']}-B{c['B']}")
+def test_chunked_prefill_matches_the_oracle(torch_cuda, ctx, cfg, gemm_mode):
+    """chunked prefill (mli_engine_cfg.prefill_chunk_positions): same schedule as the oracle's restatement of the
+    policy (iterations, pre-emptions, finish order), and -- because K and V do not depend on how a prompt was cut
+    into chunks -- the token list of every request equals the UNCHUNKED job's"""
+    torch = torch_cuda
+    try:
+        ctx.set_option(mli.OPT_GEMM_MODE, gemm_mode)
+    except mli.MliError:
+        pytest.skip("tcgen05 path not available")
+    try:
+        w = H.make_weights(131, cfg["d"], cfg["V"], cfg["S"], "Z")
+        offs, toks = H.make_prompts(133, cfg["n_req"], cfg["lo"], cfg["hi"])
+        eng = make_engine(ctx, torch, cfg, w, cfg["n_req"])
+        eng.submit(offs, toks)
+        eng.run()
+        mine, order = eng.results()
+        st = eng.stats()
+        eng.close()
+        rc, theirs, oorder, ost = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1)
+        assert rc == 0 and st.n_finished == cfg["n_req"] == ost.n_finished
+        ties, errors = H.classify_token_mismatches(w, mine, theirs)
+        assert not errors, errors[:3]
+        if gemm_mode == mli.GEMM_SIMT_EXACT:
+            assert not ties
+        if not ties:
+            assert (st.steps, st.generated_tokens, st.preemptions) == (ost.steps, ost.generated_tokens, ost.preemptions)
+            assert order.tolist() == oorder.tolist()
+        # the unchunked job: more tokens per early step, the same token lists
+        rc, plain, _, pst = H.run_oracle_engine("paged", dict(cfg, chunk=0), w, offs, toks, fix=1)
+        assert rc == 0
+        for i in plain:
+            assert np.array_equal(plain[i], theirs[i]), f"request {i}: chunking changed the oracle's tokens"
+        assert ost.steps >= pst.steps
+    finally:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+
+
+def test_chunked_prefill_bounds_the_work_of_a_step(torch_cuda, ctx):
+    """with a chunk budget no step admits-and-prefills a whole long prompt at once: the number of active rows grows
+    by at most what the budget can complete, and every row still finishes"""
+    torch = torch_cuda
+    try:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_TCGEN05)
+    except mli.MliError:
+        pytest.skip("tcgen05 path not available")
+    try:
+        cfg = dict(B=4, S=512, d=128, V=1024, n_blocks=140, n_req=4, lo=400, hi=480, max_new=3, chunk=128)
+        w = H.make_weights(141, cfg["d"], cfg["V"], cfg["S"], "Z")
+        offs, toks = H.make_prompts(143, cfg["n_req"], cfg["lo"], cfg["hi"])
+        eng = make_engine(ctx, torch, cfg, w, cfg["n_req"])
+        eng.submit(offs, toks)
+        gen = []
+        for _ in range(40):
+            eng.run(max_steps=1)
+            gen.append(eng.stats().generated_tokens)
+        eng.close()
+        # ~1760 prompt positions at 128 per step: the first token cannot appear before step ceil(400 / 128) = 4 and the
+        # four rows become active one after the other, never all in the first step
+        per_step = np.diff([0] + gen)
+        assert per_step[:3].sum() == 0 and per_step.max() <= 4
+        first = int(np.flatnonzero(per_step)[0])
+        assert first >= 3
+        assert gen[-1] == 4 * 3
+    finally:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)

@@ -85,7 +85,8 @@ def test_paged_forward_matches_reference(torch_cuda, ctx, ref, B, S, d, V, R, di
 def run_mli_engine(ctx, torch, cfg, w, offs, toks, compat):
     dw = {k: dev(torch, v) for k, v in w.items()}
     ec = mli.EngineCfg(cfg["B"], cfg["S"], cfg["d"], cfg["V"], cfg["n_blocks"], cfg.get("R", 1),
-                       compat, len(offs) - 1, None, cfg.get("max_new", 0), cfg.get("max_prefill", 0))
+                       compat, len(offs) - 1, None, cfg.get("max_new", 0), cfg.get("max_prefill", 0),
+                       cfg.get("chunk", 0))
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
     eng.submit(offs, toks)
     eng.run()
