@@ -600,6 +600,7 @@ def main():
                 # the same engine at the other BASELINE configurations, at their named shapes
                 sys.path.insert(0, str(REPO / "tools"))
                 for key, preset, kvb in (("engine_configs1", "c2a", 0), ("engine_configs1_admission_throttle", "c2a_pf", 0),
+                                         ("engine_configs1_chunked_prefill", "c2a_chunk", 0),
                                          ("engine_configs1_four_rounds", "c2a_r4", 0),
                                          ("engine_configs2", "c3", 0),
                                          ("engine_configs3", "c4", 0), ("engine_configs2_compact_kv", "c3", 1)):

@@ -29,6 +29,9 @@ PRESETS = {
     # the same with the opt-in admission throttle: at most 256 prompt positions admitted per step
     "c2a_pf": dict(B=256, d=1024, S=128, V=1024, n_req=512, lo=1, hi=64, n_blocks=1024, max_new=0, max_steps=0,
                    max_prefill=256),
+    # chunked prefill: at most 256 prompt positions prefilled per step, long prompts cut into chunks
+    "c2a_chunk": dict(B=256, d=1024, S=128, V=1024, n_req=512, lo=1, hi=64, n_blocks=1024, max_new=0, max_steps=0,
+                      chunk=256),
     # n_forward_rounds = 4: four decode rounds per scheduler iteration
     "c2a_r4": dict(B=256, d=1024, S=128, V=1024, n_req=512, lo=1, hi=64, n_blocks=1024, max_new=0, max_steps=0, R=4),
     "c3": dict(B=1024, d=2048, S=4096, V=1024, n_req=2048, lo=64, hi=2048, pool_gb=40, max_new=256, max_steps=0),
@@ -61,13 +64,13 @@ def run(name, device=0, reps=2, kv_bf16=0):
         torch.cuda.empty_cache()
         free, total = torch.cuda.mem_get_info()
         n_blocks = int((free + p["pool_gb"] * 1e9) // page_bytes)
-    ec = mli.EngineCfg(B, S, d, V, n_blocks, p.get("R", 1), 0, p["n_req"], None, p["max_new"], p.get("max_prefill", 0))
+    ec = mli.EngineCfg(B, S, d, V, n_blocks, p.get("R", 1), 0, p["n_req"], None, p["max_new"], p.get("max_prefill", 0), p.get("chunk", 0))
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
     out = {"config": name, "kv_format": "compact (K, V bf16)" if kv_bf16 else "reference (fp32)", "n_batch": B,
            "emb_dim": d, "n_sequence": S, "kv_pool_gb": n_blocks * page_bytes / 1e9, "kv_pages": n_blocks,
            "requests": p["n_req"], "prompt_lengths": f"U[{p['lo']},{p['hi']}]", "prompt_tokens": int(offs[-1]),
            "max_new_tokens": p["max_new"], "max_prefill_positions": p.get("max_prefill", 0),
-           "n_forward_rounds": p.get("R", 1)}
+           "n_forward_rounds": p.get("R", 1), "prefill_chunk_positions": p.get("chunk", 0)}
     if p["max_steps"]:
         # step 1 = admission + prefill of every prompt that fits; then a fixed number of decode steps
         eng.submit(d_offs, d_toks, is_device=True)

@@ -24,7 +24,7 @@ WORKLOAD = WORKLOADS["c2a"]
 SLOTS = ["sched_step", "encoder", "QKV+prefill GEMM", "decode attention", "logits GEMM", "decoder"]
 
 
-def measure(device=0, pdl=1, workload="c2a", world=1):
+def measure(device=0, pdl=1, workload="c2a", world=1, chunk=0):
     """one traced bench job -> (text report, dict of per-kernel in-graph times).  workload / world: the job of
     rank 0 of `bench.py --workload W` on `world` GPUs (strong workloads shrink with the world size)"""
     import bench
@@ -46,7 +46,7 @@ def measure(device=0, pdl=1, workload="c2a", world=1):
         wl["n_blocks"] = int(np.maximum((plen + wl["max_new"] + 1 + 15) // 16, 4).sum()) + 64
     wl["n_req"] = len(offs) - 1
     dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
-    ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None, wl["max_new"], 0)
+    ec = mli.EngineCfg(B, S, d, V, wl["n_blocks"], wl["R"], 0, wl["n_req"], None, wl["max_new"], 0, chunk)
     eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
     d_offs, d_toks = torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda()
     for _ in range(2):
@@ -95,6 +95,10 @@ def measure(device=0, pdl=1, workload="c2a", world=1):
     summary["attention_total_us"] = float(np.nansum(dur[:, 3]))
     summary["attention_steps"] = int(np.sum(~np.isnan(dur[:, 3])))
     lines.append(f"\nSum of means {tot:.1f} us per iteration.")
+    whole = np.nansum(dur, axis=1)
+    lines.append(f"Iteration time (us): median {np.median(whole):.1f}, p99 {np.percentile(whole, 99):.1f}, max {whole.max():.1f}"
+                 + (f"  [chunked prefill, {chunk} positions per step]" if chunk else ""))
+    summary["iteration_us_max"] = float(whole.max())
     # the merged GEMM against the rows it saw (active rows padded to 16 + 16 per prefill granule)
     rows = ((n_act + 15) // 16 * 16 + 16 * n_gran)[:real - 1]
     g = dur[:, 2]
@@ -122,8 +126,9 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--workload", default="c2a")
     ap.add_argument("--world", type=int, default=1)
+    ap.add_argument("--chunk", type=int, default=0, help="prefill_chunk_positions (0 = off)")
     args = ap.parse_args()
-    text, _ = measure(0, args.pdl, args.workload, args.world)
+    text, _ = measure(0, args.pdl, args.workload, args.world, args.chunk)
     print(text)
     if args.out:
         Path(args.out).write_text(text + "\n")
