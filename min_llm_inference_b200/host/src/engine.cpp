@@ -289,6 +289,12 @@ void run_device_job(const TensorFloat& emb_table, const TensorFloat& pos_table, 
     cfg.compat_stale_lengths = compat ? 1 : 0;
     cfg.max_requests = n_req > 0 ? n_req : 1;
     cfg.page_pool = slab;  // nullptr: the engine allocates its own pool
+    // opt-in scheduling policies of the device engine (off = the reference's behaviour), for callers of the
+    // reference's entry points: MLI_PREFILL_CHUNK / MLI_MAX_PREFILL (positions per step)
+    if (!compat) {
+        if (const char* v = std::getenv("MLI_PREFILL_CHUNK")) cfg.prefill_chunk_positions = atoi(v);
+    }
+    if (const char* v = std::getenv("MLI_MAX_PREFILL")) cfg.max_prefill_positions = atoi(v);
 
     mli_engine* engine = nullptr;
     mli::check(mli_engine_create(mli::host_context(), &cfg, emb_table.data(), pos_table.data(),
