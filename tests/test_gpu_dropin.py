@@ -63,3 +63,16 @@ def test_corrected_lengths_switch(binaries):
     assert sorted(fixed) == sorted(want)
     quirk = run(mli, paged, env={"MLI_GEMM_MODE": "1"})
     assert sorted(quirk) != sorted(want), "with 12 requests on 8 rows the quirk must show"
+
+
+def test_chunked_prefill_through_the_reference_entry_points(binaries):
+    """MLI_PREFILL_CHUNK: the drop-in's paged engine prefills prompts in chunks (device engine policy); the token
+    list of every request is the one the unchunked run produces (and the reference's non-paged engine)"""
+    mli, ref = binaries
+    paged = ["paged", 8, 128, 128, 1024, 64, 14, 30, 100, 11, "Z"]
+    env = {"MLI_FIX_STALE_LENGTHS": "1", "MLI_GEMM_MODE": "1"}
+    plain = run(mli, paged, env=env)
+    chunked = run(mli, paged, env=dict(env, MLI_PREFILL_CHUNK="32"))
+    assert sorted(plain) == sorted(chunked)
+    want = run(ref, ["dense", 8, 128, 128, 1024, 0, 14, 30, 100, 11, "Z"])
+    assert sorted(chunked) == sorted(want)
