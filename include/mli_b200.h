@@ -286,7 +286,12 @@ int mli_engine_submit(mli_engine* e, int n_req, const int* prompt_offsets, const
 int mli_engine_enqueue(mli_engine* e, int n_req, const int* prompt_offsets, const int* prompt_tokens,
                        int is_device, int* first_id);
 /* run to completion (max_steps <= 0) or for at most max_steps iterations.
- * profile_attention != 0 brackets every fused-attention launch with CUDA events (no graph). */
+ * profile_attention != 0 brackets every fused-attention launch with CUDA events (no graph).
+ * Returns MLI_ERR_NO_BLOCKS when the job cannot complete: a prompt that needs more pages than the pool
+ * holds, or a pre-empted request that has outgrown the pool (nothing resident, every page free and the
+ * queue head still not admissible).  The reference's loop (src/inferencer.cpp:43-85 over
+ * src/paged_item_storage.cpp:84-113) spins for ever in the second case; here the job ends, the requests
+ * that finished are available from mli_engine_results and the engine accepts the next mli_engine_submit. */
 int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention);
 /* download finished requests in finish order (HOST buffers): ids[n_req], offsets[n_req+1],
  * tokens[n_req * n_sequence] (prompt + generated) */

@@ -630,6 +630,14 @@ __global__ void __launch_bounds__(kSchedThreads) sched_step_kernel(SchedArgs a) 
             v->done = 1;
             *a.done_host = 1;
             __threadfence_system();
+        } else if (n_used == 0 && F == nb) {
+            // Nothing is resident, the whole pool is free and the head of the queue still was not admitted:
+            // it never will be (a pre-empted request that outgrew the pool).  The reference spins here for
+            // ever (paged_item_storage.cpp:84-113 keeps returning 0 new items); the engine ends the job
+            v->error = max(v->error, 4);
+            v->done = 1;
+            *a.done_host = 1;
+            __threadfence_system();
         } else {
             v->steps = sv.steps + 1;
             if (sv.done) {   // requests arrived after the engine had gone idle
@@ -944,6 +952,8 @@ const char* sched_error_text(int code) {
         case 1: return "engine: a token arrived for a row that is not processing";
         case 2: return "engine: a prompt length is outside [1, n_sequence - 1]";
         case 3: return "engine: a prompt needs more KV pages than the pool holds (it could never be admitted)";
+        case 4: return "engine: a pre-empted request outgrew the KV pool (it needs more pages than n_blocks) and can "
+                       "never be admitted again; the job was ended with requests still queued";
     }
     return "engine: scheduler error";
 }
@@ -1407,7 +1417,7 @@ int mli_engine_run(mli_engine* e, long long max_steps, int profile_attention) {
     e->stats.min_free_pages = hv.min_free;
     if (hv.error) {
         set_error(sched_error_text(hv.error));
-        return hv.error == 3 ? MLI_ERR_NO_BLOCKS : (hv.error == 2 ? MLI_ERR_ARG : MLI_ERR_STATE);
+        return (hv.error == 3 || hv.error == 4) ? MLI_ERR_NO_BLOCKS : (hv.error == 2 ? MLI_ERR_ARG : MLI_ERR_STATE);
     }
     return MLI_OK;
 }

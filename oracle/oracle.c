@@ -804,6 +804,10 @@ int orc_paged_engine_run(const orc_engine_cfg* cfg, const float* emb_table,
         int processing = 0;
         for (int i = 0; i < B; ++i) processing += (ps.row_req[i] >= 0);
         if (processing + rs.qcount == 0) break; /* is_done (item_storage.cpp:186-188) */
+        /* nothing resident, so the whole pool is free, and the queue head still was not admitted: a
+         * pre-empted request that outgrew the pool.  The reference spins here for ever
+         * (paged_item_storage.cpp:84-113 returns 0 new items again and again); oracle and engine stop. */
+        if (processing == 0) { rc = -5; break; }
         if (cfg->max_steps > 0 && steps >= cfg->max_steps) { rc = -4; break; }
         orc_paged_forward(ps.inp_dev, ps.len_dev, ps.idx_dev, dec, n_new, emb_table, pos_table,
                           ps.pt_dev, wk, wq, wv, attn, score, B, S, d, V, R);

@@ -258,3 +258,16 @@ def test_oracle_chunked_prefill():
     # needs corrected lengths
     rc3, *_ = H.run_oracle_engine("paged", dict(cfg, chunk=32), w, offs, toks, fix=0)
     assert rc3 == -1
+
+
+def test_oracle_stops_where_the_reference_would_spin():
+    """a request that outgrows the whole pool can never be admitted again after it pre-empted itself: the
+    reference's loop spins (paged_item_storage.cpp:84-113 keeps admitting nothing), the oracle returns -5;
+    with a token cap that keeps every request inside the pool the same job completes"""
+    cfg = dict(B=4, S=192, d=64, V=1024, n_blocks=10, R=1, n_req=6, lo=3, hi=12)
+    w = H.make_weights(81, cfg["d"], cfg["V"], cfg["S"], "Z")
+    offs, toks = H.make_prompts(83, cfg["n_req"], cfg["lo"], cfg["hi"])
+    rc, res, order, st = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1, max_steps=20000)
+    assert rc == -5 and st.n_finished < cfg["n_req"] and st.preemptions >= 1
+    rc, res, order, st = H.run_oracle_engine("paged", dict(cfg, max_new=20), w, offs, toks, fix=1, max_steps=20000)
+    assert rc == 0 and st.n_finished == cfg["n_req"]

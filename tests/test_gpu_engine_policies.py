@@ -424,3 +424,86 @@ def test_chunked_prefill_bounds_the_work_of_a_step(torch_cuda, ctx):
         assert gen[-1] == 4 * 3
     finally:
         ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+
+
+def random_engine_case(seed):
+    """one small engine job drawn from the whole policy space: table width, rounds per step, pool pressure,
+    token cap, admission throttle, chunked prefill, stale-length compatibility"""
+    r = np.random.default_rng(9000 + seed)
+    S = int(r.choice([48, 64, 96, 128, 192]))
+    d = int(r.choice([64, 128]))
+    B = int(r.integers(2, 25))
+    R = int(r.choice([1, 1, 2, 3, 5]))
+    hi = int(r.integers(2, S - 1))
+    lo = int(r.integers(1, hi + 1))
+    W = (S + 15) // 16
+    need_max = max(4, min(W, (hi + R + 15) // 16))
+    # from "every row fits twice" down to "barely one long request": the second forces pre-emption chains
+    tight = r.random() < 0.5
+    n_blocks = int(need_max + r.integers(1, max(2, B * need_max // 3 if tight else 2 * B * need_max)))
+    cfg = dict(B=B, S=S, d=d, V=1024, n_blocks=n_blocks, R=R, n_req=int(r.integers(B, 4 * B + 2)), lo=lo, hi=hi)
+    if r.random() < 0.5:
+        cfg["max_new"] = int(r.integers(1, 24))
+    if r.random() < 0.35:
+        cfg["max_prefill"] = int(r.integers(16, 4 * S))
+    compat = 0
+    if r.random() < 0.45:
+        cfg["chunk"] = int(r.choice([16, 32, 48, 64, 128, 512]))
+    elif r.random() < 0.3:
+        compat = 1        # the reference's stale lengths (quirk Q1); not combinable with chunked prefill
+    return cfg, compat
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_policy_mix_matches_the_oracle(torch_cuda, ctx, seed):
+    """exact mode: steps, tokens generated, pre-emptions, finish order and every token equal to the oracle's.
+    Some draws hold a request that outgrows the pool (the reference would spin for ever): oracle and engine
+    must both stop there, with the same requests finished"""
+    torch = torch_cuda
+    ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+    cfg, compat = random_engine_case(seed)
+    w = H.make_weights(300 + seed, cfg["d"], cfg["V"], cfg["S"], "Z" if seed % 3 else "R")
+    offs, toks = H.make_prompts(700 + seed, cfg["n_req"], cfg["lo"], cfg["hi"])
+    rc, theirs, oorder, ost = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1 - compat, max_steps=20000)
+    assert rc in (0, -5), (rc, cfg)
+    eng = make_engine(ctx, torch, cfg, w, cfg["n_req"], compat)
+    eng.submit(offs, toks)
+    if rc == -5:
+        with pytest.raises(mli.MliError, match="outgrew the KV pool"):
+            eng.run()
+    else:
+        eng.run()
+    mine, order = eng.results()
+    st = eng.stats()
+    eng.close()
+    assert (st.steps, st.generated_tokens, st.preemptions) == (ost.steps, ost.generated_tokens, ost.preemptions), cfg
+    assert order.tolist() == oorder.tolist(), "finish order differs from the oracle"
+    for i in theirs:
+        assert np.array_equal(mine[i], theirs[i]), f"request {i}: tokens differ from the oracle"
+    assert (st.n_finished == cfg["n_req"]) == (rc == 0)
+
+
+def test_request_that_outgrows_the_pool_ends_the_job(torch_cuda, ctx):
+    """12 pages per full row, 10 in the pool, no token cap: the longest-running request pre-empts itself and
+    can never come back.  The reference spins; the engine returns MLI_ERR_NO_BLOCKS with everything that could
+    finish finished, and is usable for the next job"""
+    torch = torch_cuda
+    ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+    cfg = dict(B=4, S=192, d=64, V=1024, n_blocks=10, R=1, n_req=6, lo=3, hi=12)
+    w = H.make_weights(81, cfg["d"], cfg["V"], cfg["S"], "Z")
+    offs, toks = H.make_prompts(83, cfg["n_req"], cfg["lo"], cfg["hi"])
+    rc, theirs, oorder, ost = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1, max_steps=20000)
+    assert rc == -5
+    eng = make_engine(ctx, torch, cfg, w, cfg["n_req"])
+    eng.submit(offs, toks)
+    with pytest.raises(mli.MliError, match=r"mli error -3: .*outgrew the KV pool"):   # MLI_ERR_NO_BLOCKS
+        eng.run()
+    mine, order = eng.results()
+    assert order.tolist() == oorder.tolist() and eng.stats().steps == ost.steps
+    for i in theirs:
+        assert np.array_equal(mine[i], theirs[i])
+    # the same engine with a token cap that keeps every request inside the pool
+    eng.close()
+    cfg2 = dict(cfg, max_new=20)
+    st = check_against_oracle(ctx, torch, cfg2, w, offs, toks)
+    assert st.n_finished == cfg["n_req"]
