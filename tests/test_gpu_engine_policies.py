@@ -507,3 +507,89 @@ def test_request_that_outgrows_the_pool_ends_the_job(torch_cuda, ctx):
     cfg2 = dict(cfg, max_new=20)
     st = check_against_oracle(ctx, torch, cfg2, w, offs, toks)
     assert st.n_finished == cfg["n_req"]
+
+
+@pytest.mark.parametrize("seed", range(100, 116))
+def test_random_policy_mix_tensor_core_mode(torch_cuda, ctx, seed):
+    """the same sweep through the tcgen05 GEMMs (merged QKV + prefill launch, step-by-step chunks): tokens equal
+    to the oracle's except on classified numerical ties; without a tie every scheduler decision is identical"""
+    torch = torch_cuda
+    try:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_TCGEN05)
+    except mli.MliError:
+        pytest.skip("tcgen05 path not available")
+    try:
+        cfg, _ = random_engine_case(seed)
+        cfg["d"] = 128 if seed % 2 else 256
+        cfg["n_blocks"] = max(cfg["n_blocks"], (cfg["S"] + 15) // 16 + 1)   # every request can finish
+        w = H.make_weights(300 + seed, cfg["d"], cfg["V"], cfg["S"], "Z" if seed % 3 else "R")
+        offs, toks = H.make_prompts(700 + seed, cfg["n_req"], cfg["lo"], cfg["hi"])
+        rc, theirs, oorder, ost = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1, max_steps=20000)
+        assert rc == 0, cfg
+        eng = make_engine(ctx, torch, cfg, w, cfg["n_req"])
+        eng.submit(offs, toks)
+        eng.run()
+        mine, order = eng.results()
+        st = eng.stats()
+        eng.close()
+        assert st.n_finished == cfg["n_req"]
+        ties, errors = H.classify_token_mismatches(w, mine, theirs)
+        assert not errors, (cfg, errors[:3])
+        assert len(ties) <= max(1, cfg["n_req"] // 20), (cfg, ties)
+        if not ties:
+            assert (st.steps, st.generated_tokens, st.preemptions) == (ost.steps, ost.generated_tokens, ost.preemptions)
+            assert order.tolist() == oorder.tolist()
+    finally:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+
+
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_random_arrival_schedule(torch_cuda, ctx, seed):
+    """requests arrive in random waves between slices of the run (mli_engine_enqueue / mli_engine_run(max_steps)),
+    finished ones are collected by random-sized polls: whatever the schedule, every request's tokens equal the
+    one-shot oracle job's (corrected lengths make requests independent) and the poll returns each exactly once"""
+    torch = torch_cuda
+    ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+    cfg, _ = random_engine_case(seed)
+    cfg["n_blocks"] = max(cfg["n_blocks"], (cfg["S"] + 15) // 16 + 1)
+    r = np.random.default_rng(seed)
+    w = H.make_weights(300 + seed, cfg["d"], cfg["V"], cfg["S"], "Z")
+    offs, toks = H.make_prompts(700 + seed, cfg["n_req"], cfg["lo"], cfg["hi"])
+    rc, want, _, _ = H.run_oracle_engine("paged", cfg, w, offs, toks, fix=1, max_steps=20000)
+    assert rc == 0
+
+    def part(lo, hi):
+        return (offs[lo:hi + 1] - offs[lo]).astype(np.int32), toks[offs[lo]:offs[hi]].copy()
+
+    n = cfg["n_req"]
+    cuts = sorted(set([0, n] + r.integers(1, n, size=int(r.integers(1, 5))).tolist()))
+    eng = make_engine(ctx, torch, cfg, w, n)
+    got, seen = {}, []
+
+    def poll():
+        res, ids = eng.poll_finished(max_out=int(r.integers(1, 9)))
+        for i in ids.tolist():
+            assert i not in got, f"request {i} handed out twice"
+        got.update(res)
+        seen.extend(ids.tolist())
+
+    eng.submit(*part(cuts[0], cuts[1]))
+    for a, b in zip(cuts[1:-1], cuts[2:]):
+        if r.random() < 0.7:
+            eng.run(max_steps=int(r.integers(1, 40)))
+        else:
+            eng.run()                      # idle before the next wave arrives
+        poll()
+        assert eng.enqueue(*part(a, b)) == a
+    eng.run()
+    for _ in range(4 * n + 8):
+        if len(seen) == n:
+            break
+        poll()
+    full, order = eng.results()
+    st = eng.stats()
+    eng.close()
+    assert st.n_finished == n and seen == order.tolist()
+    for i in range(n):
+        assert np.array_equal(full[i], want[i]), f"request {i}: tokens differ from the one-shot job"
+        assert np.array_equal(got[i], want[i])
