@@ -67,6 +67,7 @@ SIGNATURES = {
     "mli_version": (C.c_char_p, []),
     "mli_kernel_launch_count": (_LL, []),
     "mli_debug_set_gemm_stamps": (_I, [_P, _P]),
+    "mli_debug_last_gemm_plan": (_I, [_P, _I, _P]),
     "mli_debug_set_step_trace": (_I, [_P, _P]),
     "mli_paged_encoder": (_I, [_P] * 7 + [_I] * 4),
     "mli_prefill_kv_paged": (_I, [_P] * 6 + [_I] * 4),

@@ -1408,6 +1408,13 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
         }
         if (args.mode == TC_PREFILL || getenv("MLI_TC_FIXED_TILE")) args.bn_decode = 0;   // prefill tiles stay 256 wide
     }
+    {
+        int* lp = ctx->tc_last_plan[args.mode & 3];
+        lp[0] = pair ? 2 : args.dyn;
+        lp[1] = split;
+        lp[2] = bn;
+        lp[3] = args.bn_decode;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = args.dyn ? dim3((unsigned)(pair ? (ctx->num_sms & ~1) : ctx->num_sms), 1u, 1u)
                            : dim3((unsigned)m_tiles, (unsigned)ny, (unsigned)split);

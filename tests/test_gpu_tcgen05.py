@@ -137,3 +137,60 @@ def test_engine_tcgen05_tokens_match_reference_dense_engine(torch_cuda, tc, ref,
     theirs, _, _ = run_ref_engine(ref, "dense", case, w, offs, toks)
     bad = [i for i in range(case["n_req"]) if not np.array_equal(mine[i], theirs[i])]
     assert not bad, f"requests {bad} differ"
+
+
+def gemm_plan(ctx, kind):
+    """kind: 0 latest-token stage, 1 prefill stage, 2 logits, 3 the engine's merged step launch"""
+    import ctypes as C
+    plan = (C.c_int * 4)()
+    ctx._check(ctx.lib.mli_debug_last_gemm_plan(ctx.h, kind, plan))
+    return list(plan)
+
+
+@pytest.mark.parametrize("d", [1024, 2048])
+def test_three_launch_shapes_of_the_bulk_gemm_agree_bitwise(torch_cuda, tc, d, monkeypatch):
+    """launches of a thousand rows and more run the tcgen05 GEMM as a static grid, as a persistent launch with
+    dynamic tiles or on CTA pairs (cta_group::2).  Every output element sees the same k order, the same two
+    accumulators and the same operand rounding (cvt.rna vs its integer form) in all three, so K, V, q, the
+    logits and the tokens must be BIT-identical -- and the plan query proves each variant really ran.  The
+    engine job adds the merged launch with prefill granules (step 0 admits 1024 prompts at once)."""
+    torch = torch_cuda
+    from test_gpu_forward_engine import run_mli_engine
+    B, S, V = 1536, 16, 1024     # (the logits launch drops its K split, i.e. goes bulk, above ~1200 rows)
+    rng = np.random.default_rng(d)
+    L = rng.integers(1, S - 1, size=B).astype(np.int32)
+    L[5] = 0
+    case = H.PagedCase(1, B, S, d, L, "Z")
+    w = H.make_weights(11, d, V, S, "Z")
+    dw = {k: dev(torch, v) for k, v in w.items()}
+    attn = dev(torch, rng.random((B, d), dtype=np.float32) - 0.5)
+    job = dict(B=1024, S=64, d=d, V=V, n_blocks=1024 * 4 + 64, n_req=1100, lo=4, hi=40, R=1, max_new=3)
+    offs, toks = H.make_prompts(43, job["n_req"], job["lo"], job["hi"])
+    wj = H.make_weights(11, d, V, job["S"], "Z")      # (the job's own position table: 64 rows)
+    out = {}
+    for name, env, want in (("pairs", {}, 2), ("persistent", {"MLI_TC_NO_PAIR": "1"}, 1),
+                            ("static", {"MLI_TC_STATIC_TILES": "1"}, 0)):
+        for k in ("MLI_TC_NO_PAIR", "MLI_TC_STATIC_TILES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        pool, tab = case.device(torch)
+        dL = dev(torch, L)
+        q = torch.zeros((B, d), device="cuda")
+        tc.call("mli_qkv_latest_paged", tab, dL, dw["wk"], dw["wq"], dw["wv"], q, B, S, d)
+        scores = torch.zeros((B, V), device="cuda")
+        dec = torch.zeros((B, 1), dtype=torch.int32, device="cuda")
+        tc.call("mli_paged_decoder", attn, dw["emb"], scores, dw["pos"], tab, dL, dec, B, V, S, d, 1, 0)
+        plan_logits = gemm_plan(tc, 2)
+        tc.synchronize()
+        assert plan_logits[0] == want, (name, plan_logits)
+        mine, order, st = run_mli_engine(tc, torch, job, wj, offs, toks, compat=0)
+        plan_step = gemm_plan(tc, 3)
+        assert plan_step[0] == want and plan_step[1] == 1, (name, plan_step)
+        flat = np.concatenate([mine[i] for i in range(job["n_req"])])
+        out[name] = (pool.cpu().numpy(), q.cpu().numpy(), scores.cpu().numpy(), dec.cpu().numpy(), flat,
+                     np.asarray(order))
+    for name in ("persistent", "static"):
+        for a, b, what in zip(out["pairs"], out[name], ("pages", "q", "logits", "tokens", "engine tokens",
+                                                        "engine finish order")):
+            assert np.array_equal(a, b), f"{what}: the CTA-pair launch and the {name} launch differ"
