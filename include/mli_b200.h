@@ -95,9 +95,10 @@ long long mli_kernel_launch_count(void);
  * clock64() phase stamps [cta][8] into it (>= 8 * 8 * n_ctas bytes); NULL switches it off */
 int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev);
 /* diagnostics (tests): the plan of this context's last tcgen05 GEMM launch of one kind (0 latest-token QKV
- * stage, 1 prefill stage, 2 logits, 3 the engine's merged QKV + prefill step) into HOST int[4]:
+ * stage, 1 prefill stage, 2 logits, 3 the engine's merged QKV + prefill step) into HOST int[5]:
  * [0] kernel: 0 static grid, 1 persistent with dynamic tiles, 2 persistent on CTA pairs (cta_group::2), -1 none
- * yet; [1] K split; [2] activation-tile width; [3] decode-tile width of the pair kernel (0 = same) */
+ * yet; [1] K split; [2] activation-tile width; [3] decode-tile width of the pair kernel (0 = same); [4] K passes
+ * (emb_dim 4096 on CTA pairs: 2) */
 int mli_debug_last_gemm_plan(mli_ctx* ctx, int kind, int* plan);
 /* diagnostics (tools/step_timeline.py): when trace_dev != NULL (u64[8 + 8 * capacity], [0] = 0,
  * [1] = capacity in steps) the kernels of every engine step record the %globaltimer at which their

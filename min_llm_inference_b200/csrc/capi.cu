@@ -258,7 +258,7 @@ int mli_debug_set_gemm_stamps(mli_ctx* ctx, void* stamps_dev) {
 int mli_debug_last_gemm_plan(mli_ctx* ctx, int kind, int* plan) {
     MLI_ENTER(ctx, "null ctx");
     MLI_REQUIRE(plan != nullptr && kind >= 0 && kind < 4, "kind must be 0..3 and plan non-null");
-    for (int i = 0; i < 4; ++i) plan[i] = ctx->tc_last_plan[kind][i];
+    for (int i = 0; i < 5; ++i) plan[i] = ctx->tc_last_plan[kind][i];
     return MLI_OK;
 }
 

@@ -261,8 +261,8 @@ struct mli_ctx {
     unsigned long long* trace = nullptr;  // in-graph step timeline buffer (device), else NULL
     void* tc_dbg = nullptr;     // device buffer for GEMM phase stamps (tools/gemm_timing.py), else NULL
     // last tcgen05 GEMM launch of each kind (latest-token stage, prefill stage, logits, merged engine step):
-    // kernel (0 static grid, 1 persistent, 2 CTA pairs, -1 none yet), K split, tile width, decode tile width
-    int tc_last_plan[4][4] = {{-1, 0, 0, 0}, {-1, 0, 0, 0}, {-1, 0, 0, 0}, {-1, 0, 0, 0}};
+    // kernel (0 static grid, 1 persistent, 2 CTA pairs, -1 none yet), K split, tile width, decode tile width, K passes
+    int tc_last_plan[4][5] = {{-1, 0, 0, 0, 0}, {-1, 0, 0, 0, 0}, {-1, 0, 0, 0, 0}, {-1, 0, 0, 0, 0}};
     int opt_pdl = 1;            // MLI_OPT_PDL
     int kv_bf16 = 0;            // MLI_OPT_KV_FORMAT: 1 = compact pages (K, V in bf16)
     bool use_pdl = false;       // launch_kernel() adds programmatic stream serialization (set by the engine)

@@ -191,6 +191,9 @@ struct TcArgs {
     int dyn;               // 1 = persistent / dynamic items
     int m_tiles;           // feature tiles of the operand
     int* ctr;              // [2]: next item, CTAs finished (both back at zero when the launch ends)
+    int kv_group;          // pair kernel: feature pairs per group in the order of the prefill items (0 = all)
+    int n_pass;            // pair kernel: K is walked in n_pass passes of K / n_pass (each through the TMEM accumulators,
+                           // fp32 chains <= 1024); pass p > 0 adds its sums to what pass p - 1 stored.  <= 1: one pass
 };
 
 // optional phase stamps (clock64 of one thread per role) for tools/gemm_timing.py: [cta][8]
@@ -260,6 +263,7 @@ struct TcItems {
     int a_tiles;   // activation tiles that need all feature tiles
     int kv_tiles;  // feature tiles a pure prefill tile needs
     int n_items;
+    int p_tiles;   // pair kernel: pure prefill tiles (n_tiles - a_tiles)
 };
 __device__ __forceinline__ TcItems tc_items(const TcArgs& args, int n_valid) {
     TcItems t;
@@ -800,9 +804,16 @@ __device__ __forceinline__ TcItems tc_items_pair(const TcArgs& args, int n_valid
         t.a_tiles = n_tiles;
         t.kv_tiles = m_units;
     }
-    t.n_items = t.a_tiles * m_units + (n_tiles - t.a_tiles) * t.kv_tiles;
+    t.p_tiles = n_tiles - t.a_tiles;
+    t.n_items = t.a_tiles * m_units + t.p_tiles * t.kv_tiles;
     return t;
 }
+// Items of the prefill tiles are ordered in GROUPS of kv_group feature pairs: inside a group the activation tile is
+// the slow index, so the ~74 pairs of the GPU work on kv_group weight tiles at a time.  At emb_dim 4096 a weight
+// tile of a pair is 8 MB (hi + lo) and the K, V operand 268 MB: walking all 32 feature pairs per activation tile
+// streamed the whole operand from HBM once per 256 positions (3.8 TB over the configs[3] prefill); with groups the
+// operand is read once per group pass and the activations kv_tiles / kv_group times.  Up to emb_dim 2048 the
+// operand fits the L2 and kv_group = kv_tiles (the plain order).
 __device__ __forceinline__ void tc_item_pair(const TcArgs& args, const TcItems& t, int item, int* mu, int* nt) {
     const int m_units = args.m_tiles / 2;
     const int full = t.a_tiles * m_units;
@@ -811,8 +822,11 @@ __device__ __forceinline__ void tc_item_pair(const TcArgs& args, const TcItems& 
         *mu = item % m_units;
     } else {
         const int u = item - full;
-        *nt = t.a_tiles + u / t.kv_tiles;
-        const int k = u % t.kv_tiles, per = args.d / (2 * kBM);
+        const int G = (args.kv_group > 0 && args.kv_group < t.kv_tiles) ? args.kv_group : t.kv_tiles;
+        const int per_group = G * t.p_tiles;
+        const int g = u / per_group, r = u % per_group;
+        *nt = t.a_tiles + r / G;
+        const int k = g * G + r % G, per = args.d / (2 * kBM);
         *mu = (k < per) ? k : k + per;   // K pairs, then V pairs (the q block is skipped)
     }
 }
@@ -893,7 +907,10 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const uint32_t tmem_acc = *tmem_ptr_smem;
 
     TC_STAMP(1);
-    const int num_kb = args.K / kBK;
+    // emb_dim 4096: the two accumulators hold chains of 1024 products each, so K is walked in two passes; the second
+    // adds its sums to what the first stored (same pair, same threads' order: deterministic)
+    const int n_pass = max(1, args.n_pass);
+    const int num_kb = args.K / kBK / n_pass;       // k-blocks per pass
     const int kb_per_acc = (num_kb + args.n_acc - 1) / args.n_acc;
     const int n_pre = (item >= n_items) ? 0 : min(nst, num_kb);
     const uint64_t w_policy = l2_policy_evict_last();
@@ -910,14 +927,14 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     trace_stamp(args.trace, args.trace_slot);
 
     const int n_valid = tc_n_valid(args);
-    uint32_t it = 0, tile_iter = 0;
+    uint32_t it = 0, tile_iter = 0, item_iter = 0;   // k-blocks / accumulator rounds (passes) / items so far
     while (item < n_items) {
         // the leader claims the pair's NEXT item and leaves it in both CTAs; it is read after the cluster
         // barrier that ends this tile
         if (leader && tid == 0) {
             const int nxt = n_pairs + atomicAdd(&args.ctr[0], 1);
-            s_next_item[tile_iter & 1] = nxt;
-            st_dsmem_i32(dsmem_addr(&s_next_item[tile_iter & 1], 1), nxt);
+            s_next_item[item_iter & 1] = nxt;
+            st_dsmem_i32(dsmem_addr(&s_next_item[item_iter & 1], 1), nxt);
         }
         const int n0 = nt * bn;
         const int n_eff = min(bn, ((n_valid - n0) + 15) & ~15);   // UMMA N of this tile
@@ -929,6 +946,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         }
         __syncthreads();
 
+        for (int pass = 0; pass < n_pass; ++pass) {
+        const int kb0 = pass * num_kb;   // first k-block of the pass
         if (warp == 0) {
             // ===================== TMA producer (this CTA's weight tile) =====================
             if (lane == 0) {
@@ -937,7 +956,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     if (tile_iter == 0 && kb < n_pre) continue;   // issued before the wait
                     const int s = i % nst;
                     mbar_wait(&empty_bar[s], ((i / nst) & 1) ^ 1);
-                    load_weights(s, kb);
+                    load_weights(s, kb0 + kb);
                 }
             }
             __syncwarp();
@@ -1021,7 +1040,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 float4 raw[kRows];
 #pragma unroll
                 for (int i = 0; i < kRows; ++i)
-                    raw[i] = rp[i] ? ldg_stream(rp[i] + kb * (kBK / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    raw[i] = rp[i] ? ldg_stream(rp[i] + (kb0 + kb) * (kBK / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const int s = i2 % nst;
                 const long long t0 = c_dbg ? clock64() : 0;
                 if (lane == 0) mbar_wait(&empty_bar[s], ((i2 / nst) & 1) ^ 1);   // one poller per warp
@@ -1095,7 +1114,14 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             for (int n = tid >> 5; n < n_eff; n += kTcThreadsV2 / 32) {
                 float* p = dst_tab[n];
                 if (p == nullptr) continue;
-                const float4 v = *reinterpret_cast<const float4*>(part + (size_t)n * kBM + f4 * 4);
+                float4 v = *reinterpret_cast<const float4*>(part + (size_t)n * kBM + f4 * 4);
+                if (pass > 0) {   // (never with bf16 rows: the host plans passes for fp32 destinations only)
+                    const float4 o = reinterpret_cast<const float4*>(p + plane)[f4];
+                    v.x += o.x;
+                    v.y += o.y;
+                    v.z += o.z;
+                    v.w += o.w;
+                }
                 if (to_bf16) {
                     const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
                     uint2 u;
@@ -1113,7 +1139,9 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         tc_fence_after();
         it += (uint32_t)num_kb;
         ++tile_iter;
-        item = s_next_item[(tile_iter - 1) & 1];
+        }   // pass
+        ++item_iter;
+        item = s_next_item[(item_iter - 1) & 1];
         if (item < n_items) {
             int mu;
             tc_item_pair(args, s_items, item, &mu, &nt);
@@ -1329,15 +1357,41 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     // accuracy before occupancy: the TMEM holds 512 / bn accumulators, and a single fp32 chain should
     // not exceed 1024 products (truncating accumulation: 2048-long chains on all-positive data drift
     // 1.4e-5).  With wide tiles and K >= 2048 that takes a K split even when one wave would not need it.
+    // The engine's merged step launch on CTA pairs keeps split == 1 and walks K in passes instead (second pass adds to
+    // what the first stored): emb_dim 4096 then runs the same persistent bulk kernel as 1024 / 2048 (the cluster
+    // split-K plan measured 0.63 of the tf32 peak on the configs[3] prefill against 0.85 for the bulk kernel)
+    int n_pass = 1;
     {
         const int acc_max = std::max(1, 512 / ((bn + 31) / 32 * 32));
-        while (args.K / (split * acc_max) > 1024 && split < (args.defer ? kMaxLogitSplit : 8) &&
+        const bool pass_ok = split == 1 && args.mode == TC_STEP && bn == kMaxBN && !ctx->kv_bf16 && m_tiles % 2 == 0 &&
+                             (args.d / kBM) % 2 == 0 && !getenv("MLI_TC_STATIC_TILES") && !getenv("MLI_TC_NO_PAIR") &&
+                             !getenv("MLI_TC_NO_KPASS");
+        if (pass_ok && args.K / acc_max > 1024) {
+            for (int p = 2; p <= 8; p *= 2)
+                if (num_kb % p == 0 && args.K / (p * acc_max) <= 1024) {
+                    n_pass = p;
+                    break;
+                }
+        }
+        while (n_pass == 1 && args.K / (split * acc_max) > 1024 && split < (args.defer ? kMaxLogitSplit : 8) &&
                num_kb % (2 * split) == 0)
             split *= 2;
     }
+    args.n_pass = n_pass;
+    args.kv_group = 0;
+    if (args.mode == TC_STEP) {
+        // weight tile of a pair: 256 features x K x (hi + lo); keep a group within ~32 MB of the L2 (configs[3] prefill: groups of 2 / 4 / 8 / 16 / 32 pairs = 1.29 / 1.27 / 1.29 / 1.34 / 1.53 s)
+        const long long tile_bytes = 256LL * args.K * 8;
+        const int kv_tiles = args.d / kBM;
+        int g = (int)std::max<long long>(1, (32LL << 20) / tile_bytes);
+        if (const char* e = getenv("MLI_TC_KV_GROUP")) g = atoi(e);
+        while (g > 1 && kv_tiles % g) --g;
+        if (g >= 1 && g < kv_tiles) args.kv_group = g;
+    }
     // a deferred-reduce launch (logits) that ends up without a K split is a plain bulk GEMM over thousands of
     // rows: full-width tiles, persistent launch (measured at 8192 rows: 190 us as 512 CTAs of 128 x 128 tiles)
-    if (args.defer && split == 1 && plan_rows >= 4 * kMaxBN) bn = kMaxBN;
+    // (only while two accumulators of 256 columns keep the chains at 1024: emb_dim <= 2048)
+    if (args.defer && split == 1 && plan_rows >= 4 * kMaxBN && args.K <= 2048) bn = kMaxBN;
     int ny = n_tiles_all;
     const int cap = std::max(1, ctx->num_sms / (m_tiles * split));
     if (ny > cap) ny = std::max(cap, std::min(n_tiles_plan, n_tiles_all));
@@ -1349,11 +1403,11 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     if (args.mode == TC_STEP && args.use_gran) ny = std::max(ny, std::min(2, n_tiles_all));
     args.bn = bn;
     args.acc_stride = (bn + 31) / 32 * 32;
-    const int k_per_cta = args.K / split;
+    const int k_per_cta = args.K / split / n_pass;
     int n_acc = (k_per_cta + 511) / 512;           // fp32 chains of at most 512 (see kChunks note above)
     if (n_acc > 512 / args.acc_stride) n_acc = 512 / args.acc_stride;
     if (n_acc < 1) n_acc = 1;
-    if (n_acc > num_kb / split) n_acc = num_kb / split;
+    if (n_acc > num_kb / split / n_pass) n_acc = num_kb / split / n_pass;
     args.n_acc = n_acc;
     int cols = 32;
     while (cols < n_acc * args.acc_stride) cols <<= 1;
@@ -1389,6 +1443,10 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
     args.bn_decode = 0;
     const bool pair = args.dyn && m_tiles % 2 == 0 && (args.mode == TC_LOGITS || (args.d / kBM) % 2 == 0) &&
                       args.n_acc * args.acc_stride <= 512 && !getenv("MLI_TC_NO_PAIR");
+    if (n_pass > 1 && !pair) {
+        set_error("tcgen05 GEMM plan: K passes need the CTA-pair kernel");
+        return MLI_ERR_STATE;
+    }
     if (pair) {
         int rc0 = ensure_dyn_smem(ctx, gemm_tf32x3_pair_kernel, tc_smem_bytes(kPairStages, kPairHalf));
         if (rc0) return rc0;
@@ -1414,6 +1472,7 @@ int run_gemm(mli_ctx* ctx, const OperandEntry* w, TcArgs args, int m_tiles, int 
         lp[1] = split;
         lp[2] = bn;
         lp[3] = args.bn_decode;
+        lp[4] = n_pass;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = args.dyn ? dim3((unsigned)(pair ? (ctx->num_sms & ~1) : ctx->num_sms), 1u, 1u)
