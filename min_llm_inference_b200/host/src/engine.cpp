@@ -303,9 +303,13 @@ void run_device_job(const TensorFloat& emb_table, const TensorFloat& pos_table, 
         fin_toks(static_cast<size_t>(n_req > 0 ? n_req : 1) * n_sequence);
     int n_fin = 0;
     mli_engine_stats stats{};
+    int run_rc = MLI_OK;
     try {
         mli::check(mli_engine_submit(engine, n_req, offsets.data(), tokens.data(), 0));
-        mli::check(mli_engine_run(engine, 0, 0));
+        // a job that cannot complete (a request outgrew the pool: the reference would spin) still hands back
+        // what did finish before the exception below
+        run_rc = mli_engine_run(engine, 0, 0);
+        if (run_rc != MLI_ERR_NO_BLOCKS) mli::check(run_rc);
         mli::check(mli_engine_results(engine, fin_ids.data(), fin_offs.data(), fin_toks.data(), &n_fin));
         mli::check(mli_engine_get_stats(engine, &stats));
     } catch (...) {
@@ -318,6 +322,7 @@ void run_device_job(const TensorFloat& emb_table, const TensorFloat& pos_table, 
         item_storage.add_finished_item(IdTokensPair(
             reqs[q].first, std::vector<int>(fin_toks.begin() + fin_offs[k], fin_toks.begin() + fin_offs[k + 1])));
     }
+    if (run_rc != MLI_OK) throw std::runtime_error("No enough block memories to return");
     const auto t1 = std::chrono::high_resolution_clock::now();
     ThroughputCounter& counter = get_global_throughput_counter();
     counter.add_job(stats.generated_tokens, std::chrono::duration<double>(t1 - t0).count());
