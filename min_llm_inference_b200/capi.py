@@ -308,7 +308,7 @@ class Engine:
         n, S = self.n_req, self.cfg.n_sequence
         ids = np.zeros(n, np.int32)
         offs = np.zeros(n + 1, np.int32)
-        toks = np.zeros(n * S, np.int32)
+        toks = np.empty(n * S, np.int32)     # only [0, offs[n_finished]) is written and read
         nf = _I()
         self.ctx._check(self.lib.mli_engine_results(self.h, ids.ctypes.data, offs.ctypes.data,
                                                     toks.ctypes.data, C.byref(nf)))
