@@ -200,8 +200,13 @@ def reference_arm(args, rank, world, wl):
     # decode iterations each (the reference's host prefill of ONE 1056-token prompt at emb_dim 1024 is
     # ~9 GFLOP of scalar loops; the whole 8192-request job would take hours)
     n_sample = min(cores, n_total)
+    # ... taken at the MEDIAN prompt length of the set (ties by id): every core then works for the whole step (with
+    # the first `cores` requests the step lasted as long as its one ~2000-token prompt and the other cores idled,
+    # which both understated the reference and made a 20-step run take six minutes)
+    plen = np.diff(offs)
+    pick = np.argsort(np.abs(plen - np.median(plen)), kind="stable")[:n_sample]
     tasks = []
-    for k in range(n_sample):
+    for k in pick.tolist():
         o = (offs[k:k + 2] - offs[k]).astype(np.int32)
         tasks.append((o, toks[offs[k]:offs[k + 1]].copy(), iters))
     have_ref = H.ref_available()
@@ -212,12 +217,14 @@ def reference_arm(args, rank, world, wl):
         except Exception:
             have_ref = False
     kind = "reference" if have_ref else "port"
-    sample = (f"first {n_sample} of {n_total} requests, one per host core ({cores} processes), prefill + {iters} "
-              f"engine iterations per step; same emb_dim / n_sequence / vocab / prompt distribution as the GPU arm")
+    sample = (f"the {n_sample} requests of {n_total} closest to the median prompt length ({int(np.median(plen))} tokens), one "
+              f"per host core ({cores} processes), prefill + {iters} engine iterations per step; same emb_dim / "
+              f"n_sequence / vocab as the GPU arm")
     ctx = mp.get_context("spawn")
     times, gens = [], []
     with ctx.Pool(n_sample, initializer=_ref_worker_init, initargs=(wl["d"], wl["V"], wl["S"], have_ref)) as pool:
-        pool.map(_ref_worker_run, [(t[0], t[1], 1) for t in tasks[:n_sample]])   # page in libraries / contexts
+        # page in libraries / contexts on an 8-token prompt
+        pool.map(_ref_worker_run, [(np.array([0, 8], np.int32), t[1][:8].copy(), 1) for t in tasks])
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             res = pool.map(_ref_worker_run, tasks, chunksize=1)
