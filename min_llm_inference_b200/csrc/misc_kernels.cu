@@ -7,6 +7,8 @@
 #include "encoder_body.cuh"
 
 #include <cfloat>
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 
 namespace mli {
 
@@ -289,40 +291,40 @@ qkt_unfused_kernel(const float* __restrict__ q, float* const* __restrict__ page_
     if (tid < np) qkt[(size_t)r * S + j0 + tid] = acc / sqrtf((float)d);
 }
 
-// one CTA per row: p_j = expf(x_j - max) * (1.f / sum) for j < L, zeros up to S
+// One warp per row, in the arithmetic order of the reference's kernel (self_attention_inference_optimized.cu:191-242)
+// so that the probabilities are BIT-identical to it: lane t walks the groups of four scores t, t + 32, ... keeping a
+// running (max, sum) pair -- the sum is rescaled by expf(old max - new max) once per group, then the group's terms are
+// added in index order; the lanes' pairs are merged with the toolkit's own warp reduction (cg::reduce, the same
+// primitive and therefore the same tree as the reference's build); p_j = expf(x_j - max) * (1.f / sum).
 __global__ void __launch_bounds__(256)
-softmax_lengths_unfused_kernel(float* __restrict__ qkt, const int* __restrict__ lengths, int S) {
-    __shared__ float red[8];
-    __shared__ float bc;
-    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = min(lengths[r], S);
+softmax_lengths_unfused_kernel(float* __restrict__ qkt, const int* __restrict__ lengths, int B, int S) {
+    namespace cg = cooperative_groups;
+    const cg::thread_block_tile<32> warp = cg::tiled_partition<32>(cg::this_thread_block());
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= B) return;
+    const int L = lengths[r];
     float* row = qkt + (size_t)r * S;
-    float m = -INFINITY;
-    for (int j = tid; j < L; j += 256) m = fmaxf(m, row[j]);
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    if (tid == 0) {
-        float t = red[0];
-        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
-        bc = t;
+    float m = -FLT_MAX, s = 0.f;
+    for (int g = lane; 4 * g < L; g += 32) {
+        const int n = min(4, L - 4 * g);
+        const float4 x4 = reinterpret_cast<const float4*>(row)[g];
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float before = m;
+        for (int j = 0; j < n; ++j) m = fmaxf(m, x[j]);
+        s *= expf(before - m);
+        for (int j = 0; j < n; ++j) s += expf(x[j] - m);
     }
-    __syncthreads();
-    m = bc;
-    float s = 0.f;
-    for (int j = tid; j < L; j += 256) s += expf(row[j] - m);
-    s = warp_sum(s);
-    __syncthreads();
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    if (tid == 0) {
-        float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += red[i];
-        bc = 1.f / t;
+    const float m_all = cg::reduce(warp, m, cg::greater<float>());
+    s *= expf(m - m_all);
+    const float inv = 1.f / cg::reduce(warp, s, cg::plus<float>());
+    for (int g = lane; g < S / 4; g += 32) {
+        const float4 x4 = reinterpret_cast<const float4*>(row)[g];
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+        float p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = (4 * g + j < L) ? expf(x[j] - m_all) * inv : 0.f;
+        reinterpret_cast<float4*>(row)[g] = make_float4(p[0], p[1], p[2], p[3]);
     }
-    __syncthreads();
-    const float inv = bc;
-    for (int j = tid; j < S; j += 256) row[j] = (j < L) ? expf(row[j] - m) * inv : 0.f;
 }
 
 // grid (ceil(d / 256), B), 256 threads: thread = one output column, positions ascending
@@ -356,7 +358,7 @@ int launch_qkt_unfused(mli_ctx* ctx, const float* q, float* const* page_table, c
 }
 
 int launch_softmax_lengths_unfused(mli_ctx* ctx, float* qkt, const int* lengths, int B, int S) {
-    softmax_lengths_unfused_kernel<<<B, 256, 0, ctx->stream>>>(qkt, lengths, S);
+    softmax_lengths_unfused_kernel<<<(B + 7) / 8, 256, 0, ctx->stream>>>(qkt, lengths, B, S);
     MLI_LAUNCH_CHECK();
     return 0;
 }
