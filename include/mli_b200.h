@@ -137,7 +137,7 @@ int mli_decode_attention_paged(mli_ctx* ctx, const float* q, float* const* page_
 
 /* The reference's three unfused stages, one launch each, for callers (and the reference's kernel tests,
  * tests/paged_attention_kernels_test.cpp:115-169) written against them.  Not used by the product path.
- * They keep the reference's summation order, so scores and P.V are bit-identical to its kernels.
+ * They keep the reference's arithmetic order, so scores, probabilities and P.V are bit-identical to its kernels.
  * replaces launch_qkt_paged_attention (paged_attention.h:37-39; paged_attention.cu:208-280):
  * qkt_output[r][j] = (q[r] . K[r][j]) / sqrtf(d) for j < lengths[r]; other entries untouched */
 int mli_qkt_paged(mli_ctx* ctx, const float* q, float* const* page_table, const int* lengths,
