@@ -1,7 +1,7 @@
 // kernels_driver.cpp -- the KERNEL-level half of the drop-in claim (engine_driver.cpp is the engine-level half).
 // ONE source written purely against the reference's kernel launchers and page-table classes
-//   include/kernels/encoder.h:16-25, include/kernels/paged_attention.h:17-67,
-//   include/kernels/self_attention_inference_optimized.h:21-22, include/kernels/decoder.h:27-31,
+//   include/kernels/encoder.h:5-25, include/kernels/paged_attention.h:17-67,
+//   include/kernels/self_attention_inference_optimized.h:21-50, include/kernels/decoder.h:19-31,
 //   include/paged_item_storage.h:10-46, include/tensor.hpp
 // i.e. the calls the reference's tests/paged_attention_kernels_test.cpp, encoder_test.cpp and decoder_test.cpp
 // make (those need gtest, which is not installed, and unseeded fixtures; this driver feeds fixed tensors).
@@ -93,7 +93,7 @@ uint64_t hash_pages(const std::vector<std::vector<float*>>& pages, const std::ve
 
 int main(int argc, char** argv) {
     if (argc < 7) {
-        fprintf(stderr, "usage: %s B S d V seed dist(R|Z)\n", argv[0]);
+        fprintf(stderr, "usage: %s B S d V seed dist(R|Z) [dense]\n", argv[0]);
         return 2;
     }
     const size_t B = atoi(argv[1]), S = atoi(argv[2]), d = atoi(argv[3]), V = atoi(argv[4]);
@@ -121,6 +121,65 @@ int main(int argc, char** argv) {
     TensorInt lengths = int_tensor(len, {B});
     TensorInt inp_dev = int_tensor(inp, {B, S});
     TensorInt new_items = int_tensor(new_idx, {B});
+
+    if (argc > 7 && std::string(argv[7]) == "dense") {
+        // ---- the non-paged path (configs[0]): encoder.h:16-20, self_attention_inference_optimized.h:28-50,
+        //      decoder.h:19-25 on the dense layouts inp_embedding[B,S,d], kt_cache[B,d,S], v_cache[B,S,d] ----
+        TensorFloat inp_embedding({B, S, d}, DeviceType::DEVICE), kt_cache({B, d, S}, DeviceType::DEVICE),
+            v_cache({B, S, d}, DeviceType::DEVICE);
+        cudaMemset(inp_embedding.data(), 0, B * S * d * sizeof(float));
+        cudaMemset(kt_cache.data(), 0, B * S * d * sizeof(float));
+        cudaMemset(v_cache.data(), 0, B * S * d * sizeof(float));
+        launch_inference_optimized_encoder_kernel(emb_table.data(), pos_table.data(), inp_dev.data(),
+                                                  inp_embedding.data(), lengths.data(), new_items.data(),
+                                                  static_cast<int>(B), static_cast<int>(S), static_cast<int>(d), n_new);
+        TensorFloat q_output({B, d}, DeviceType::DEVICE), qkt({B, S}, DeviceType::DEVICE),
+            attention({B, d}, DeviceType::DEVICE);
+        cudaMemset(q_output.data(), 0, B * d * sizeof(float));
+        cudaMemset(attention.data(), 0, B * d * sizeof(float));
+        inference_self_attention(inp_embedding, lengths, wk, wq, wv, new_items, kt_cache, v_cache, q_output, qkt,
+                                 attention, n_new);
+        {
+            const std::vector<float> e = to_host(inp_embedding.data(), B * S * d), kt = to_host(kt_cache.data(), B * S * d),
+                                     v = to_host(v_cache.data(), B * S * d), q = to_host(q_output.data(), B * d);
+            uint64_t he = 1469598103934665603ULL, hk = he, hv = he, hq = he;
+            for (size_t r = 0; r < B; ++r) {
+                he = fnv(e.data() + r * S * d, len[r] * d * sizeof(float), he);
+                hv = fnv(v.data() + r * S * d, len[r] * d * sizeof(float), hv);
+                for (size_t k = 0; k < d; ++k) hk = fnv(kt.data() + (r * d + k) * S, len[r] * sizeof(float), hk);
+                if (len[r] > 0) hq = fnv(q.data() + r * d, d * sizeof(float), hq);
+            }
+            printf("HASH encoder %016llx\nHASH k_cache %016llx\nHASH v_cache %016llx\nHASH q %016llx\n",
+                   (unsigned long long)he, (unsigned long long)hk, (unsigned long long)hv, (unsigned long long)hq);
+            const std::vector<float> a = to_host(attention.data(), B * d);
+            printf("VALS attention");
+            for (size_t r = 0; r < B; ++r)
+                for (size_t c = 0; c < d; c += d / 4) printf(" %.9g", a[r * d + c]);
+            printf("\n");
+        }
+        // decoder on a GIVEN activation (the two attention blocks agree to 1e-4, not to the bit)
+        TensorFloat given = random_tensor({B, d}, rng, 1.0f, shift);
+        TensorFloat emb_score({B, V}, DeviceType::DEVICE);
+        TensorInt decoder_result = int_tensor(std::vector<int>(B, -7), {B});
+        launch_decoder(given, emb_table, emb_score, pos_table, inp_embedding, lengths, decoder_result);
+        const std::vector<float> sc = to_host(emb_score.data(), B * V);
+        uint64_t h = 1469598103934665603ULL;
+        for (size_t r = 0; r < B; ++r)
+            if (len[r] > 0) h = fnv(sc.data() + r * V, V * sizeof(float), h);
+        printf("HASH logits %016llx\n", (unsigned long long)h);
+        const std::vector<int> tok = to_host(decoder_result.data(), B), new_len = to_host(lengths.data(), B);
+        printf("TOKENS");
+        for (int t : tok) printf(" %d", t);
+        printf("\nLENGTHS");
+        for (int l : new_len) printf(" %d", l);
+        printf("\n");
+        const std::vector<float> e2 = to_host(inp_embedding.data(), B * S * d);
+        uint64_t h2 = 1469598103934665603ULL;
+        for (size_t r = 0; r < B; ++r)
+            if (new_len[r] > 0) h2 = fnv(e2.data() + (r * S + len[r]) * d, d * sizeof(float), h2);
+        printf("HASH next_embedding %016llx\n", (unsigned long long)h2);
+        return 0;
+    }
 
     // pages: every row gets a full table row, in an order that is not the slab's
     MemoryBlockManager blocks(static_cast<int>(B * W), PAGE_BLOCK_SIZE * 3 * d);

@@ -131,3 +131,21 @@ def test_same_source_same_kernel_results(torch_cuda, case, dist):
     tc = run_kernels(KMLI, args, env={"MLI_GEMM_MODE": "0"})
     assert np.abs(np.asarray(tc["paged_attention"]) - b).max() <= 1e-4 * scale
     assert tc["LENGTHS"] == theirs["LENGTHS"]
+
+
+@pytest.mark.parametrize("case", [(32, 256, 256, 1024, 6), (9, 64, 128, 1024, 7)], ids=lambda c: f"B{c[0]}-S{c[1]}-d{c[2]}")
+@pytest.mark.parametrize("dist", ["R", "Z"])
+def test_same_source_same_dense_kernel_results(torch_cuda, case, dist):
+    """the non-paged launchers (configs[0] shape first): dense encoder, inference_self_attention, launch_decoder --
+    embeddings, K^T / V caches, q, logits, next embedding bit-identical; attention at rel 1e-4; tokens, lengths equal"""
+    if not KMLI.exists() or not KREF.exists():
+        pytest.skip("kernel-level drop-in drivers not built")
+    import numpy as np
+    args = list(case) + [dist, "dense"]
+    theirs = run_kernels(KREF, args)
+    mine = run_kernels(KMLI, args, env={"MLI_GEMM_MODE": "1"})
+    for s in ["encoder", "k_cache", "v_cache", "q", "logits", "next_embedding"]:
+        assert mine[s] == theirs[s], f"dense stage {s}: bits differ from the reference's kernel"
+    assert mine["TOKENS"] == theirs["TOKENS"] and mine["LENGTHS"] == theirs["LENGTHS"]
+    a, b = np.asarray(mine["attention"]), np.asarray(theirs["attention"])
+    assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
