@@ -198,6 +198,63 @@ int main(int argc, char** argv) {
     manager.maybe_flush_changes();
     TensorFloatPoint& page_table = manager.get_page_table_device();
 
+    if (argc > 7 && std::string(argv[7]) == "cublas") {
+        // ---- the warp-tiling + cuBLAS twins (paged_attention.h:46-67, decoder.h:34-37): the reference's fast build.
+        //      Their summation order is cuBLAS's, so nothing here is compared by bits: VALS lines, rel 1e-4 ----
+        cublasHandle_t handle;
+        if (cublasCreate(&handle) != CUBLAS_STATUS_SUCCESS) return 6;
+        launch_paged_attention_encoder_kernel(emb_table.data(), pos_table.data(), inp_dev.data(), page_table.data(),
+                                              lengths.data(), new_items.data(), static_cast<int>(B),
+                                              static_cast<int>(S), static_cast<int>(d), n_new);
+        TensorFloat q_output({B, d}, DeviceType::DEVICE), qkt({B, S}, DeviceType::DEVICE),
+            attention({B, d}, DeviceType::DEVICE), latest_emb({B, d}, DeviceType::DEVICE),
+            placeholder({B, d}, DeviceType::DEVICE);
+        cudaMemset(q_output.data(), 0, B * d * sizeof(float));
+        cudaMemset(attention.data(), 0, B * d * sizeof(float));
+        cudaMemset(latest_emb.data(), 0, B * d * sizeof(float));
+        paged_attention_with_cublas(page_table, lengths, wk, wq, wv, new_items, q_output, qkt, attention, latest_emb,
+                                    placeholder, n_new, static_cast<int>(S), handle);
+        auto sample_pages = [&](const char* name, int which) {
+            printf("VALS %s", name);
+            for (size_t r = 0; r < B; ++r)
+                for (int j = 0; j < len[r]; j += 5) {
+                    const std::vector<float> row = to_host(
+                        pages[r][j / PAGE_BLOCK_SIZE] + static_cast<size_t>(j % PAGE_BLOCK_SIZE) * 3 * d + which * d, d);
+                    for (size_t c = 0; c < d; c += d / 4) printf(" %.9g", row[c]);
+                }
+            printf("\n");
+        };
+        sample_pages("k_cache", 1);
+        sample_pages("v_cache", 2);
+        const std::vector<float> q = to_host(q_output.data(), B * d), a = to_host(attention.data(), B * d);
+        printf("VALS q");
+        for (size_t r = 0; r < B; ++r)
+            if (len[r] > 0)
+                for (size_t c = 0; c < d; c += d / 8) printf(" %.9g", q[r * d + c]);
+        printf("\nVALS attention");
+        for (size_t r = 0; r < B; ++r)
+            for (size_t c = 0; c < d; c += d / 8) printf(" %.9g", a[r * d + c]);
+        printf("\n");
+        TensorFloat emb_score({B, V}, DeviceType::DEVICE);
+        TensorInt decoder_result = int_tensor(std::vector<int>(B, -7), {B, 1});
+        launch_paged_attention_cublas_decoder_multi_rounds(attention, emb_table, emb_score, pos_table, page_table,
+                                                           lengths, decoder_result, 0, handle);
+        const std::vector<float> sc = to_host(emb_score.data(), B * V);
+        printf("VALS logits");
+        for (size_t r = 0; r < B; ++r)
+            if (len[r] > 0)
+                for (size_t c = 0; c < V; c += V / 8) printf(" %.9g", sc[r * V + c]);
+        printf("\n");
+        const std::vector<int> tok = to_host(decoder_result.data(), B), new_len = to_host(lengths.data(), B);
+        printf("TOKENS");
+        for (int t : tok) printf(" %d", t);
+        printf("\nLENGTHS");
+        for (int l : new_len) printf(" %d", l);
+        printf("\n");
+        cublasDestroy(handle);
+        return 0;
+    }
+
     // ---- stage by stage (the reference's unfused chain) ----
     launch_paged_attention_encoder_kernel(emb_table.data(), pos_table.data(), inp_dev.data(), page_table.data(),
                                           lengths.data(), new_items.data(), static_cast<int>(B), static_cast<int>(S),

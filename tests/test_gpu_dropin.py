@@ -149,3 +149,24 @@ def test_same_source_same_dense_kernel_results(torch_cuda, case, dist):
     assert mine["TOKENS"] == theirs["TOKENS"] and mine["LENGTHS"] == theirs["LENGTHS"]
     a, b = np.asarray(mine["attention"]), np.asarray(theirs["attention"])
     assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("case", KERNEL_CASES, ids=lambda c: f"B{c[0]}-S{c[1]}-d{c[2]}")
+@pytest.mark.parametrize("dist", ["R", "Z"])
+@pytest.mark.parametrize("gemm_mode", ["1", "0"], ids=["simt_exact", "tcgen05"])
+def test_same_source_cublas_twins(torch_cuda, case, dist, gemm_mode):
+    """the reference's fast build (warp-tiling prefill + cuBLAS latest-QKV / logits, paged_attention_with_cublas,
+    the cuBLAS decoder) from the same source: cuBLAS's summation order is its own, so K, V, q, attention and logits
+    are compared at rel 1e-4 (the reference's own tests use abs 1e-3 there), tokens and lengths exactly"""
+    if not KMLI.exists() or not KREF.exists():
+        pytest.skip("kernel-level drop-in drivers not built")
+    import numpy as np
+    args = list(case) + [dist, "cublas"]
+    theirs = run_kernels(KREF, args)
+    mine = run_kernels(KMLI, args, env={"MLI_GEMM_MODE": gemm_mode})
+    for s in ["k_cache", "v_cache", "q", "attention", "logits"]:
+        a, b = np.asarray(mine[s]), np.asarray(theirs[s])
+        assert a.shape == b.shape and a.size > 0
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max(), f"{s}: rel err {np.abs(a - b).max() / np.abs(b).max():.2e}"
+    assert mine["LENGTHS"] == theirs["LENGTHS"]
+    assert mine["TOKENS"] == theirs["TOKENS"]
