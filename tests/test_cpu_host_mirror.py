@@ -34,4 +34,5 @@ def test_host_mirror_exports_reference_api():
 def test_drop_in_driver_compiles_against_the_mirror():
     subprocess.run(["make", "-C", str(REPO / "tests" / "dropin"), "mli"], check=True,
                    stdout=subprocess.DEVNULL)
-    assert (REPO / "tests" / "dropin" / "_build" / "dropin_driver_mli").exists()
+    for name in ("dropin_driver_mli", "dropin_stepwise_mli", "dropin_kernels_mli"):
+        assert (REPO / "tests" / "dropin" / "_build" / name).exists(), name

@@ -170,3 +170,39 @@ def test_same_source_cublas_twins(torch_cuda, case, dist, gemm_mode):
         assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max(), f"{s}: rel err {np.abs(a - b).max() / np.abs(b).max():.2e}"
     assert mine["LENGTHS"] == theirs["LENGTHS"]
     assert mine["TOKENS"] == theirs["TOKENS"]
+
+
+# ---- step level: tests/dropin/stepwise_driver.cpp (the caller writes the engine loop itself) ------------------
+SMLI = REPO / "tests" / "dropin" / "_build" / "dropin_stepwise_mli"
+SREF = REPO / "oracle" / "_ref" / "dropin_stepwise_ref"
+
+# kind, B, S, d, V, n_blocks, n_req, lo, hi, seed, dist, rounds
+STEP_CASES = [
+    ("dense", 8, 64, 128, 1024, 0, 20, 1, 40, 21, "Z", 1),
+    ("paged", 8, 128, 128, 1024, 64, 20, 1, 60, 22, "Z", 1),
+    ("paged", 8, 128, 128, 1024, 30, 22, 20, 64, 23, "Z", 1),     # pool pressure: growth, tail pre-emption
+    ("paged", 6, 64, 128, 1024, 40, 14, 1, 30, 24, "R", 3),       # three decode rounds per scheduler step
+    ("paged", 12, 128, 256, 1024, 50, 30, 10, 64, 25, "Z", 2),
+]
+
+
+@pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: f"{c[0]}-B{c[1]}-blocks{c[5]}-R{c[11]}")
+def test_same_source_same_decisions_step_by_step(torch_cuda, case):
+    """a user-written engine loop over the reference's scheduling API (insert_new_items, forward,
+    process_decoder_result, allocate_or_free_memory_blocks_if_needed): after EVERY iteration the rows admitted, rows
+    finished, tokens, device lengths (stale-length quirk included), free-page count and each resident row's page list
+    (slab indices, i.e. the physical order of the free list) are identical to the reference build's, and so are the
+    final token lists"""
+    if not SMLI.exists() or not SREF.exists():
+        pytest.skip("step-level drop-in drivers not built")
+    e = dict(os.environ, MLI_GEMM_MODE="1")
+    outs = []
+    for binary in (SREF, SMLI):
+        out = subprocess.run([str(binary)] + [str(a) for a in case], capture_output=True, text=True, env=e, timeout=600)
+        assert out.returncode == 0, f"{binary.name} failed: {out.stderr[-2000:]}"
+        outs.append([l for l in out.stdout.splitlines() if l.split(" ")[0] in ("STEP", "ITERATIONS", "RESULT")])
+    theirs, mine = outs
+    assert any(l.startswith("STEP") for l in theirs) and sum(l.startswith("RESULT") for l in theirs) == case[6]
+    for a, b in zip(mine, theirs):
+        assert a == b, f"first difference:\nours: {a[:400]}\nref:  {b[:400]}"
+    assert len(mine) == len(theirs)
