@@ -62,3 +62,84 @@ def test_engine_at_configs2_dims_vs_reference_dense_engine(torch_cuda, ctx, refe
               f"{len(ties)} tie flips")
     finally:
         ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+
+
+def test_headline_job_at_full_size(torch_cuda, ctx):
+    """The bench's own job -- BASELINE configs[4] on one GPU: 8192 rows, 8192 requests U[64,2048], emb_dim 1024,
+    n_sequence 2304, 128 new tokens each, ~120 GB of fp32 KV pages, tensor-core mode -- checked where a whole-job
+    oracle run is out of reach (hours of CPU):
+      * against the CPU oracle on a SAMPLE of its requests (shortest, longest and ten more), each run alone: requests
+        are independent with corrected lengths, so their token lists must match the big job's (numerical ties classified);
+      * size-independent properties of every request: prompt kept as prefix, at most 128 new tokens, fewer only after
+        EOF; nothing pre-empted (the pool holds every request), every page back in the pool at the end;
+      * idempotence: the same job again on the same engine gives the same tokens bit for bit."""
+    torch = torch_cuda
+    import os
+    import bench
+    torch.cuda.empty_cache()
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 140e9:
+        pytest.skip(f"needs ~125 GB of free HBM, {free_b / 1e9:.0f} GB free")
+    try:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_TCGEN05)
+    except mli.MliError:
+        pytest.skip("tcgen05 path not available")
+    try:
+        wl = dict(bench.WORKLOADS["c4"])
+        B, S, d, V, cap = wl["B"], wl["S"], wl["d"], wl["V"], wl["max_new"]
+        offs, toks, n_total = bench.rank_requests(wl, 0, 1)
+        n_req = len(offs) - 1
+        assert (B, n_req, n_total) == (8192, 8192, 8192)
+        plen = np.diff(offs).astype(np.int64)
+        n_blocks = int(np.maximum((plen + cap + 1 + 15) // 16, 4).sum()) + 64
+        w = H.make_weights(bench.SEED_W, d, V, S, "Z")
+        dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+        ec = mli.EngineCfg(B, S, d, V, n_blocks, wl["R"], 0, n_req, None, cap, 0, 0)
+        eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+        runs = []
+        for _ in range(2):
+            eng.submit(offs, toks)
+            eng.run()
+            res, order = eng.results()
+            st = eng.stats()
+            runs.append((res, order.copy(), (st.steps, st.generated_tokens, st.preemptions, st.n_finished,
+                                             st.peak_resident_rows, st.min_free_pages)))
+        eng.close()
+        (mine, order, stats), (again, order2, stats2) = runs
+        # idempotence (fixed reduction orders; a page that did not return to the pool would change min_free_pages)
+        assert stats == stats2 and np.array_equal(order, order2)
+        assert all(np.array_equal(mine[i], again[i]) for i in range(n_req))
+        steps, generated, preempt, n_fin, peak_rows, min_free = stats
+        assert (n_fin, preempt, peak_rows) == (n_req, 0, B) and min_free >= 64 and steps == cap
+        # per-request properties
+        total_new = 0
+        for i in range(n_req):
+            t = mine[i]
+            p = toks[offs[i]:offs[i + 1]]
+            assert np.array_equal(t[:len(p)], p), f"request {i}: prompt not kept"
+            new = len(t) - len(p)
+            assert 1 <= new <= cap
+            assert new == cap or t[-1] == mli.EOF_TOKEN_ID, f"request {i}: stopped after {new} tokens without EOF"
+            assert not np.any(t[len(p):-1] == mli.EOF_TOKEN_ID)
+            total_new += new
+        assert total_new == generated
+        # the oracle on a sample of the requests, each as its own row of a small job
+        rng = np.random.default_rng(5)
+        sample = sorted(set([int(np.argmin(plen)), int(np.argmax(plen))] + rng.choice(n_req, 10, replace=False).tolist()))
+        s_offs = np.zeros(len(sample) + 1, np.int32)
+        s_toks = []
+        for k, i in enumerate(sample):
+            s_toks.append(toks[offs[i]:offs[i + 1]])
+            s_offs[k + 1] = s_offs[k] + len(s_toks[-1])
+        s_toks = np.concatenate(s_toks).astype(np.int32)
+        cfg = dict(B=len(sample), S=S, d=d, V=V, n_blocks=len(sample) * (S // 16), R=1, max_new=cap)
+        rc, want, _, _ = H.run_oracle_engine("paged", cfg, w, s_offs, s_toks, fix=1, threads=min(16, os.cpu_count() or 8))
+        assert rc == 0 and len(want) == len(sample)
+        got = {k: mine[i] for k, i in enumerate(sample)}
+        ties, errors = H.classify_token_mismatches(w, got, want)
+        assert not errors, f"(sample index, position, margin) differ from the oracle beyond a numerical tie: {errors[:4]}"
+        assert len(ties) <= 1, f"too many tie flips in a sample of {len(sample)}: {ties}"
+        print(f"headline job: {generated} tokens, sample of {len(sample)} requests vs oracle: {len(ties)} tie flips")
+    finally:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+        torch.cuda.empty_cache()
