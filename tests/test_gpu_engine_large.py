@@ -143,3 +143,77 @@ def test_headline_job_at_full_size(torch_cuda, ctx):
     finally:
         ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
         torch.cuda.empty_cache()
+
+
+def test_configs2_job_at_full_size(torch_cuda, ctx):
+    """BASELINE configs[2] as the bench runs it (tools/run_config.py c3): 1024 rows, emb_dim 2048, n_sequence 4096,
+    2048 requests U[64,2048], 256-token cap, 40 GB of KV pages -- continuous batching in which the pool, not the row
+    count, limits admission (512 iterations for two waves of requests).  Same three checks as the headline job: a request sample against the CPU oracle
+    (each alone in a roomy pool: tokens do not depend on the schedule), per-request properties, idempotence."""
+    torch = torch_cuda
+    import os
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import run_config
+    p = run_config.PRESETS["c3"]
+    torch.cuda.empty_cache()
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 60e9:
+        pytest.skip(f"needs ~45 GB of free HBM, {free_b / 1e9:.0f} GB free")
+    try:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_TCGEN05)
+    except mli.MliError:
+        pytest.skip("tcgen05 path not available")
+    try:
+        B, S, d, V, cap, n_req = p["B"], p["S"], p["d"], p["V"], p["max_new"], p["n_req"]
+        assert (B, S, d, n_req, p["lo"], p["hi"], cap) == (1024, 4096, 2048, 2048, 64, 2048, 256)
+        n_blocks = int(p["pool_gb"] * 1e9 // (16 * 3 * d * 4))
+        w = H.make_weights(1001, d, V, S, "Z")
+        offs, toks = H.make_prompts(2002, n_req, p["lo"], p["hi"])
+        dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+        ec = mli.EngineCfg(B, S, d, V, n_blocks, 1, 0, n_req, None, cap, 0, 0)
+        eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+        runs = []
+        for _ in range(2):
+            eng.submit(offs, toks)
+            eng.run()
+            res, order = eng.results()
+            st = eng.stats()
+            runs.append((res, order.copy(), (st.steps, st.generated_tokens, st.preemptions, st.n_finished,
+                                             st.peak_resident_rows, st.min_free_pages)))
+        eng.close()
+        (mine, order, stats), (again, order2, stats2) = runs
+        assert stats == stats2 and np.array_equal(order, order2)
+        assert all(np.array_equal(mine[i], again[i]) for i in range(n_req))
+        steps, generated, preempt, n_fin, peak_rows, min_free = stats
+        assert n_fin == n_req and peak_rows <= B and min_free >= 0
+        total_new = 0
+        for i in range(n_req):
+            t, pr = mine[i], toks[offs[i]:offs[i + 1]]
+            assert np.array_equal(t[:len(pr)], pr), f"request {i}: prompt not kept"
+            new = len(t) - len(pr)
+            assert 1 <= new <= cap and (new == cap or t[-1] == mli.EOF_TOKEN_ID)
+            total_new += new
+        # (a pre-empted request generates its tokens once: they travel with it as the new prompt)
+        assert total_new == generated
+        plen = np.diff(offs)
+        rng = np.random.default_rng(6)
+        sample = sorted(set([int(np.argmin(plen)), int(np.argmax(plen))] + rng.choice(n_req, 6, replace=False).tolist()))
+        s_offs = np.zeros(len(sample) + 1, np.int32)
+        parts = []
+        for k, i in enumerate(sample):
+            parts.append(toks[offs[i]:offs[i + 1]])
+            s_offs[k + 1] = s_offs[k] + len(parts[-1])
+        s_toks = np.concatenate(parts).astype(np.int32)
+        cfg = dict(B=len(sample), S=S, d=d, V=V, n_blocks=len(sample) * (S // 16), R=1, max_new=cap)
+        rc, want, _, _ = H.run_oracle_engine("paged", cfg, w, s_offs, s_toks, fix=1, threads=min(16, os.cpu_count() or 8))
+        assert rc == 0 and len(want) == len(sample)
+        ties, errors = H.classify_token_mismatches(w, {k: mine[i] for k, i in enumerate(sample)}, want)
+        assert not errors, f"(sample index, position, margin) differ from the oracle beyond a numerical tie: {errors[:4]}"
+        assert len(ties) <= 1, f"too many tie flips in a sample of {len(sample)}: {ties}"
+        print(f"configs[2] job: {generated} tokens, {steps} iterations, {preempt} pre-emptions, "
+              f"sample of {len(sample)} vs oracle: {len(ties)} tie flips")
+    finally:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+        torch.cuda.empty_cache()
