@@ -72,7 +72,9 @@ def test_headline_job_at_full_size(torch_cuda, ctx):
         are independent with corrected lengths, so their token lists must match the big job's (numerical ties classified);
       * size-independent properties of every request: prompt kept as prefix, at most 128 new tokens, fewer only after
         EOF; nothing pre-empted (the pool holds every request), every page back in the pool at the end;
-      * idempotence: the same job again on the same engine gives the same tokens bit for bit."""
+      * idempotence: the same job again on the same engine gives the same tokens bit for bit;
+      * sharding: rank 3 of the 8-GPU run (1024 rows, its balanced deal of requests) reproduces the one-GPU job's
+        token lists for its requests."""
     torch = torch_cuda
     import os
     import bench
@@ -140,6 +142,23 @@ def test_headline_job_at_full_size(torch_cuda, ctx):
         assert not errors, f"(sample index, position, margin) differ from the oracle beyond a numerical tie: {errors[:4]}"
         assert len(ties) <= 1, f"too many tie flips in a sample of {len(sample)}: {ties}"
         print(f"headline job: {generated} tokens, sample of {len(sample)} requests vs oracle: {len(ties)} tie flips")
+        # strong scaling shards the SAME request set: rank 3 of 8 (1024 rows, its prompt-length-balanced deal of 1024
+        # requests) must produce, for its requests, the token lists of the one-GPU job
+        from min_llm_inference_b200.sharding import shard_requests_balanced
+        l_offs, l_toks, ids = shard_requests_balanced(offs, toks, 3, 8)
+        l_plen = np.diff(l_offs).astype(np.int64)
+        l_blocks = int(np.maximum((l_plen + cap + 1 + 15) // 16, 4).sum()) + 64
+        ec8 = mli.EngineCfg(B // 8, S, d, V, l_blocks, wl["R"], 0, len(ids), None, cap, 0, 0)
+        eng8 = mli.Engine(ctx, ec8, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+        eng8.submit(l_offs, l_toks)
+        eng8.run()
+        shard, _ = eng8.results()
+        eng8.close()
+        assert len(ids) == n_req // 8
+        ties8, errors8 = H.classify_token_mismatches(w, shard, {k: mine[int(i)] for k, i in enumerate(ids)})
+        assert not errors8, errors8[:4]
+        assert len(ties8) <= len(ids) // 100, f"too many tie flips between the sharded and the one-GPU job: {ties8}"
+        print(f"rank 3 of 8 vs the one-GPU job: {len(ties8)} tie flips in {len(ids)} requests")
     finally:
         ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
         torch.cuda.empty_cache()
