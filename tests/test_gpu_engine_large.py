@@ -236,3 +236,67 @@ def test_configs2_job_at_full_size(torch_cuda, ctx):
     finally:
         ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
         torch.cuda.empty_cache()
+
+
+def test_configs3_dimensions_tensor_core_vs_exact_order(torch_cuda, ctx):
+    """BASELINE configs[3] dimensions (emb_dim 4096, n_sequence 32768, prompts U[24000,32511]) with 32 of its 128 rows
+    (51 GB of pages instead of 181 GB; the GEMM plan is the same one: CTA pairs, two K passes, grouped item order).
+    A CPU oracle run of one such request is ~2 TFLOP of scalar loops, so the witness is the engine's own exact-order
+    mode -- whose K, V, q, logits are bit-identical to the reference's naive kernels (tests/test_gpu_stages.py) -- on
+    four of the requests: same token lists, numerical ties classified by a float64 replay."""
+    torch = torch_cuda
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import run_config
+    p = run_config.PRESETS["c4"]
+    torch.cuda.empty_cache()
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 75e9:
+        pytest.skip(f"needs ~60 GB of free HBM, {free_b / 1e9:.0f} GB free")
+    B, S, d, V, cap, n_req = 32, p["S"], p["d"], p["V"], 8, 32
+    assert (S, d, p["lo"], p["hi"]) == (32768, 4096, 24000, 32511)
+    w = H.make_weights(1001, d, V, S, "Z")
+    offs, toks = H.make_prompts(2002, n_req, p["lo"], p["hi"])
+    dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+
+    def job(mode, rows, o, t):
+        ctx.set_option(mli.OPT_GEMM_MODE, mode)
+        n = len(o) - 1
+        ec = mli.EngineCfg(rows, S, d, V, rows * (S // 16), 1, 0, n, None, cap, 0, 0)
+        eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+        eng.submit(o, t)
+        eng.run()
+        res, _ = eng.results()
+        st = eng.stats()
+        eng.close()
+        return res, st
+
+    try:
+        try:
+            mine, st = job(mli.GEMM_TCGEN05, B, offs, toks)
+        except mli.MliError:
+            pytest.skip("tcgen05 path not available")
+        import ctypes as C
+        plan = (C.c_int * 5)()
+        ctx._check(ctx.lib.mli_debug_last_gemm_plan(ctx.h, 3, plan))
+        assert list(plan)[:2] == [2, 1] and plan[4] == 2, f"expected CTA pairs with two K passes, got {list(plan)}"
+        assert st.n_finished == n_req and st.preemptions == 0
+        sample = [0, 7, 19, 31]
+        s_offs = np.zeros(len(sample) + 1, np.int32)
+        parts = []
+        for k, i in enumerate(sample):
+            parts.append(toks[offs[i]:offs[i + 1]])
+            s_offs[k + 1] = s_offs[k] + len(parts[-1])
+        want, _ = job(mli.GEMM_SIMT_EXACT, len(sample), s_offs, np.concatenate(parts).astype(np.int32))
+        for k, i in enumerate(sample):
+            new = len(mine[i]) - (offs[i + 1] - offs[i])
+            assert 1 <= new <= cap
+        ties, errors = H.classify_token_mismatches(w, {k: mine[i] for k, i in enumerate(sample)}, want)
+        assert not errors, f"(sample index, position, margin) differ from the exact-order mode beyond a tie: {errors[:4]}"
+        assert len(ties) <= 1, ties
+        print(f"configs[3] dims: {st.generated_tokens} tokens after {int(offs[-1])} prompt positions, "
+              f"{len(ties)} tie flips against the exact-order mode")
+    finally:
+        ctx.set_option(mli.OPT_GEMM_MODE, mli.GEMM_SIMT_EXACT)
+        torch.cuda.empty_cache()
