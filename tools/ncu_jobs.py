@@ -8,6 +8,8 @@
                                                  # (+ 768 short ones) at emb_dim 1024: a prefill-sized launch of the
                                                  # merged tcgen05 GEMM (~0.5 M positions, 2 TFLOP fp32-equivalent) on a
                                                  # 6 GB pool, small enough for --set full
+    python tools/ncu_jobs.py prefill_d4096       # the same at emb_dim 4096 (16 prompts of 24-32 k tokens): K passes and the
+                                                 # grouped item order; MLI_TC_KV_GROUP=32 = plain order for the A/B
     python tools/ncu_jobs.py attn_one            # ONE fused-attention launch, B=1024, d=1024, L~U[64,2176] (9.5 GB)
 """
 import json
@@ -145,6 +147,33 @@ def attn_one():
     ctx.close()
 
 
+def prefill_d4096():
+    """one engine step at emb_dim 4096 that admits 16 prompts of 24-32 k tokens (configs[3] dimensions, ~0.45 M
+    positions, 23 GB of pages): the merged GEMM on CTA pairs with two K passes.  MLI_TC_KV_GROUP=32 in the environment
+    selects the plain item order (all 32 feature pairs of an activation tile, then the next tile) for the A/B of the
+    DRAM traffic"""
+    torch.cuda.set_device(0)
+    ctx = mli.Context(0, torch.cuda.current_stream().cuda_stream)
+    B, S, d, V, n_req = 16, 32768, 4096, 1024, 16
+    w = H.make_weights(1001, d, V, S, "Z")
+    offs, toks = H.make_prompts(2002, n_req, 24000, 32511)
+    dw = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    ec = mli.EngineCfg(B, S, d, V, B * (S // 16), 1, 0, n_req, None, 2, 0)
+    eng = mli.Engine(ctx, ec, dw["emb"], dw["pos"], dw["wk"], dw["wq"], dw["wv"])
+    ms = []
+    for rep in range(2):
+        eng.submit(torch.from_numpy(offs).cuda(), torch.from_numpy(toks).cuda(), is_device=True)
+        eng.run(max_steps=1)
+        ms.append(eng.stats().gpu_ms)
+    pos = int(offs[-1])
+    print(json.dumps({"emb_dim": d, "prompt_positions": pos, "step_ms": ms,
+                      "fp32_equivalent_tflop": 4.0 * pos * d * d / 1e12,
+                      "algorithmic_bytes": {"activations_read": 4.0 * pos * d, "kv_written": 8.0 * pos * d,
+                                            "weights_hi_lo": 2 * 3 * 4.0 * d * d}}), flush=True)
+    eng.close()
+    ctx.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "attn_job":
@@ -153,5 +182,7 @@ if __name__ == "__main__":
         prefill()
     elif what == "prefill_stamps":
         prefill(stamps=True)
+    elif what == "prefill_d4096":
+        prefill_d4096()
     else:
         attn_one()

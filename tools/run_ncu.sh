@@ -24,3 +24,9 @@ python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_r2_bench_plain
 $NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file gpurun_out/ncu_r2_launches_c4.csv python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_r2_bench_ncu.log 2>&1
 echo "launch list rc=$?"
 ls -la gpurun_out/ | grep ncu_r2
+# 5. emb_dim 4096 prefill launch: DRAM traffic and tensor-pipe activity with the grouped item order and with the plain one
+python tools/ncu_jobs.py prefill_d4096 > gpurun_out/ncu_r2_prefill4096_plain.json 2> gpurun_out/ncu_r2_prefill4096_plain.err || exit 1
+M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct
+$NCU --metrics $M -k regex:gemm_tf32x3_pair --csv --log-file gpurun_out/ncu_r2_prefill4096_grouped.csv python tools/ncu_jobs.py prefill_d4096 > /dev/null 2>&1
+MLI_TC_KV_GROUP=32 $NCU --metrics $M -k regex:gemm_tf32x3_pair --csv --log-file gpurun_out/ncu_r2_prefill4096_plainorder.csv python tools/ncu_jobs.py prefill_d4096 > /dev/null 2>&1
+echo "prefill d4096 rc=$?"
